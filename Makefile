@@ -1,0 +1,32 @@
+# Builds libbbme.so (sm_100a only) in-tree, the CPU oracle, and (when /root/reference exists) oracle/_ref.
+NVCC ?= /usr/local/cuda/bin/nvcc
+PKG := blockbasedmotionestimation_b200
+CSRC := $(PKG)/csrc
+NVFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function \
+           --fmad=false -Iinclude
+LIB := $(PKG)/libbbme.so
+OBJS := $(CSRC)/kernels.o $(CSRC)/search_tma.o $(CSRC)/capi.o $(CSRC)/flo.o
+
+all: $(LIB) oracle
+
+$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/kernels.h include/bbme.h
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@
+
+$(CSRC)/flo.o: $(CSRC)/flo.cpp include/bbme.h
+	g++ -O2 -ffp-contract=off -fPIC -std=c++17 -Wall -Iinclude -c $< -o $@
+
+$(LIB): $(OBJS)
+	$(NVCC) -shared -o $@ $(OBJS) -cudart static
+
+oracle:
+	$(MAKE) -C oracle
+
+micro: bench_micro/int_peak
+bench_micro/int_peak: bench_micro/int_peak.cu
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o $@ $<
+
+clean:
+	rm -f $(OBJS) $(LIB)
+	$(MAKE) -C oracle clean
+
+.PHONY: all oracle clean micro

@@ -1,0 +1,332 @@
+"""Python mirror of the reference's C++ interface for the hot path, on top of the C ABI.
+
+Reference interface being mirrored (file:line of /root/reference):
+  class MF              motion_framework.h:9-54   ctor (:12), calcMotionBlockMatching (:13), public ints (:16-19)
+  class PyramidLevel    pyramid_level.h:7-16
+  class BlockPosition   block_position.h:4-9
+  class Flow            rw_flow.h:9-38            ReadFlowFile, WriteFlowFile, CalculateMSE
+Error behaviour: where the reference prints and exit(1)s, these raise BbmeError carrying the same text.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import BbmeOptions, BbmeShape, BbmeStats
+
+
+class BbmeError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"[bbme status {status}] {message}")
+        self.status = status
+
+
+def _int_array(values):
+    return (C.c_int * len(values))(*[int(v) for v in values])
+
+
+def _check(lib, ctx, rc, what):
+    if rc != 0:
+        msg = lib.bbme_last_error(ctx)
+        msg = msg.decode() if msg else ""
+        if not msg:
+            msg = lib.bbme_status_string(rc).decode()
+        raise BbmeError(rc, f"{what}: {msg}")
+
+
+def _shape_dict(sh):
+    L = sh.num_levels
+    return {
+        "width": sh.width, "height": sh.height,
+        "padded_width": sh.padded_width, "padded_height": sh.padded_height,
+        "padding_x": sh.padding_x, "padding_y": sh.padding_y, "num_levels": L,
+        "level_width": list(sh.level_width[:L]), "level_height": list(sh.level_height[:L]),
+        "block_size": list(sh.block_size[:L]), "search_size": list(sh.search_size[:L]),
+    }
+
+
+def plan_shape(width, height, search_size, block_size, num_levels=None):
+    """Padding search of MF::MF (motion_framework.cpp:15-54); needs no GPU."""
+    lib = _lib.load()
+    L = len(block_size) if num_levels is None else int(num_levels)
+    sh = BbmeShape()
+    rc = lib.bbme_plan_shape(int(width), int(height), L, _int_array(search_size[:L]), _int_array(block_size[:L]), C.byref(sh))
+    if rc != 0:
+        raise BbmeError(rc, lib.bbme_status_string(rc).decode())
+    return _shape_dict(sh)
+
+
+class PyramidLevel:
+    """pyramid_level.h:7-16 -- per-level state; images/flow are fetched from the device on demand."""
+
+    def __init__(self, block_size, search_size, lam, width, height):
+        self.block_size = block_size
+        self.search_size = search_size
+        self.lambda_ = lam  # `lambda` is a Python keyword
+        self.width = width
+        self.height = height
+        self.image1 = None
+        self.image2 = None
+        self.level_flow = None
+
+
+class BlockPosition:
+    """block_position.h:4-9"""
+
+    def __init__(self, pos_x=0, pos_y=0):
+        self.pos_x = pos_x
+        self.pos_y = pos_y
+
+
+class Estimator:
+    """A planned context: one GPU, fixed geometry, batched estimation (bbme_plan / bbme_estimate*)."""
+
+    def __init__(self, width, height, search_size, block_size, num_levels=None, sweeps=2, device=0, chunk_pairs=1,
+                 slots=1, search_kernel=0, collect_stats=False, keep_search_mv=False):
+        self._lib = _lib.load()
+        self._ctx = C.c_void_p()
+        rc = self._lib.bbme_create(C.byref(self._ctx), int(device))
+        if rc != 0:
+            msg = self._lib.bbme_last_error(None)
+            raise BbmeError(rc, "bbme_create: " + (msg.decode() if msg else ""))
+        L = len(block_size) if num_levels is None else int(num_levels)
+        opt = BbmeOptions()
+        self._lib.bbme_default_options(C.byref(opt))
+        opt.sweeps = int(sweeps)
+        opt.chunk_pairs = int(chunk_pairs)
+        opt.slots = int(slots)
+        opt.search_kernel = int(search_kernel)
+        opt.collect_stats = int(bool(collect_stats))
+        opt.keep_search_mv = int(bool(keep_search_mv))
+        sh = BbmeShape()
+        try:
+            _check(self._lib, self._ctx,
+                   self._lib.bbme_plan(self._ctx, int(width), int(height), L, _int_array(search_size[:L]),
+                                       _int_array(block_size[:L]), C.byref(opt), C.byref(sh)), "bbme_plan")
+        except Exception:
+            self.close()
+            raise
+        self._sh = sh
+        self.shape = _shape_dict(sh)
+        self.chunk_pairs = int(chunk_pairs)
+        self.device = int(device)
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self._lib.bbme_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- host-buffer API (H2D + pipeline + D2H inside the call)
+    def flow_shape(self):
+        return (self.shape["padded_height"], self.shape["padded_width"], 2)
+
+    def estimate(self, im1, im2, out=None):
+        return self.estimate_batch([im1], [im2], None if out is None else [out])[0]
+
+    def estimate_batch(self, im1_list, im2_list, out_list=None):
+        n = len(im1_list)
+        h, w = self.shape["height"], self.shape["width"]
+        pitch = None
+        keep = []
+        p1 = (C.c_void_p * n)()
+        p2 = (C.c_void_p * n)()
+        po = (C.c_void_p * n)()
+        if out_list is None:
+            out_list = [np.empty(self.flow_shape(), np.float32) for _ in range(n)]
+        for i in range(n):
+            a, b, o = im1_list[i], im2_list[i], out_list[i]
+            for img in (a, b):
+                if img.dtype != np.uint8 or img.ndim != 2 or img.shape != (h, w) or img.strides[1] != 1:
+                    raise BbmeError(-1, f"frames must be uint8 {h}x{w} with unit column stride")
+            if pitch is None:
+                pitch = a.strides[0]
+            if a.strides[0] != pitch or b.strides[0] != pitch:
+                raise BbmeError(-1, "all frames of a batch must share one row pitch")
+            if o.dtype != np.float32 or o.shape != self.flow_shape() or not o.flags["C_CONTIGUOUS"]:
+                raise BbmeError(-1, "flow buffers must be C-contiguous float32 (padded_h, padded_w, 2)")
+            keep += [a, b, o]
+            p1[i], p2[i], po[i] = a.ctypes.data, b.ctypes.data, o.ctypes.data
+        _check(self._lib, self._ctx, self._lib.bbme_estimate_batch(self._ctx, n, p1, p2, pitch, po), "bbme_estimate_batch")
+        return out_list
+
+    # -- device-resident API (raw device pointers, e.g. torch tensors' data_ptr())
+    def estimate_device(self, n, d_im1, d_im2, pitch, plane, d_flow, flow_plane):
+        _check(self._lib, self._ctx,
+               self._lib.bbme_estimate_device(self._ctx, int(n), C.c_void_p(d_im1), C.c_void_p(d_im2), int(pitch),
+                                              int(plane), C.c_void_p(d_flow), int(flow_plane)), "bbme_estimate_device")
+
+    def estimate_device_compact(self, n, d_im1, d_im2, pitch, plane, d_mv, mv_plane):
+        _check(self._lib, self._ctx,
+               self._lib.bbme_estimate_device_compact(self._ctx, int(n), C.c_void_p(d_im1), C.c_void_p(d_im2), int(pitch),
+                                                      int(plane), C.c_void_p(d_mv), int(mv_plane)),
+               "bbme_estimate_device_compact")
+
+    def sync(self):
+        _check(self._lib, self._ctx, self._lib.bbme_sync(self._ctx), "bbme_sync")
+
+    def stats(self):
+        st = BbmeStats()
+        _check(self._lib, self._ctx, self._lib.bbme_get_stats(self._ctx, C.byref(st)), "bbme_get_stats")
+        return {k: getattr(st, k) for k, _ in BbmeStats._fields_}
+
+    # -- state of the last call (per-stage parity tests)
+    def level_image(self, level, frame, pair=0):
+        out = np.empty((self.shape["level_height"][level], self.shape["level_width"][level]), np.uint8)
+        _check(self._lib, self._ctx, self._lib.bbme_debug_level_image(self._ctx, pair, frame, level, out.ctypes.data),
+               "bbme_debug_level_image")
+        return out
+
+    def level_mv(self, level, which=0, pair=0):
+        g = 2 if which == 0 else self.shape["block_size"][level]
+        out = np.empty((self.shape["level_height"][level] // g, self.shape["level_width"][level] // g, 2), np.int16)
+        _check(self._lib, self._ctx, self._lib.bbme_debug_level_mv(self._ctx, pair, level, which, out.ctypes.data),
+               "bbme_debug_level_mv")
+        return out
+
+    # -- single stages on host arrays
+    def stage_pyrdown(self, src):
+        src = np.ascontiguousarray(src, np.uint8)
+        h, w = src.shape
+        dst = np.empty((h // 2, w // 2), np.uint8)
+        _check(self._lib, self._ctx, self._lib.bbme_stage_pyrdown(self._ctx, src.ctypes.data, w, h, dst.ctypes.data), "stage_pyrdown")
+        return dst
+
+    def stage_search(self, im1, im2, block_size, search_size, pred=None, kernel=0):
+        im1 = np.ascontiguousarray(im1, np.uint8)
+        im2 = np.ascontiguousarray(im2, np.uint8)
+        h, w = im1.shape
+        mv = np.zeros((h // block_size, w // block_size, 2), np.int16) if pred is None else np.ascontiguousarray(pred, np.int16).copy()
+        st = BbmeStats()
+        _check(self._lib, self._ctx,
+               self._lib.bbme_stage_search(self._ctx, im1.ctypes.data, im2.ctypes.data, w, h, block_size, search_size,
+                                           mv.ctypes.data, kernel, C.byref(st)), "stage_search")
+        return mv, {k: getattr(st, k) for k, _ in BbmeStats._fields_}
+
+    def stage_regularize(self, im1, im2, block_size, lam, mult, mv):
+        im1 = np.ascontiguousarray(im1, np.uint8)
+        im2 = np.ascontiguousarray(im2, np.uint8)
+        h, w = im1.shape
+        mv = np.ascontiguousarray(mv, np.int16).copy()
+        rounds = C.c_uint32(0)
+        _check(self._lib, self._ctx,
+               self._lib.bbme_stage_regularize(self._ctx, im1.ctypes.data, im2.ctypes.data, w, h, block_size, float(lam),
+                                               int(mult), mv.ctypes.data, C.byref(rounds)), "stage_regularize")
+        return mv, rounds.value
+
+    def stage_divide(self, mv):
+        mv = np.ascontiguousarray(mv, np.int16)
+        gh, gw, _ = mv.shape
+        out = np.empty((2 * gh, 2 * gw, 2), np.int16)
+        _check(self._lib, self._ctx, self._lib.bbme_stage_divide(self._ctx, mv.ctypes.data, gw, gh, out.ctypes.data), "stage_divide")
+        return out
+
+    def stage_copy_mvs(self, coarse_mv2, coarse_block_size, fine_block_size):
+        coarse_mv2 = np.ascontiguousarray(coarse_mv2, np.int16)
+        ch2, cw2, _ = coarse_mv2.shape
+        cw, ch = 2 * cw2, 2 * ch2
+        out = np.empty((2 * ch // fine_block_size, 2 * cw // fine_block_size, 2), np.int16)
+        _check(self._lib, self._ctx,
+               self._lib.bbme_stage_copy_mvs(self._ctx, coarse_mv2.ctypes.data, cw, ch, coarse_block_size, fine_block_size,
+                                             out.ctypes.data), "stage_copy_mvs")
+        return out
+
+
+class MF:
+    """Mirror of `class MF` (motion_framework.h:9-54).
+
+    MF(image1, image2, search_size, block_size, num_levels) builds the padded pyramid on the GPU (the
+    reference's constructor, motion_framework.cpp:4-111, does pad + pyrDown); calcMotionBlockMatching()
+    returns the padded CV_32FC2-shaped field (motion_framework.cpp:218).  `sweeps` exposes the hard-coded 2
+    of motion_framework.cpp:143,184.
+    """
+
+    def __init__(self, image1, image2, search_size, block_size, num_levels, sweeps=2, device=0, **opts):
+        if num_levels <= 0:
+            raise BbmeError(-1, "num_levels must be > 0")  # assert(num_levels > 0), motion_framework.cpp:7
+        image1 = np.asarray(image1)
+        image2 = np.asarray(image2)
+        if image1.shape != image2.shape:
+            raise BbmeError(-1, "image1 and image2 differ in size")  # assert, motion_framework.cpp:8
+        h, w = image1.shape
+        self._est = Estimator(w, h, list(search_size)[:num_levels], list(block_size)[:num_levels], num_levels,
+                              sweeps=sweeps, device=device, **opts)
+        sh = self._est.shape
+        self.padded_height = sh["padded_height"]
+        self.padded_width = sh["padded_width"]
+        self.padding_x = sh["padding_x"]
+        self.padding_y = sh["padding_y"]
+        self._im1 = np.ascontiguousarray(image1, np.uint8)
+        self._im2 = np.ascontiguousarray(image2, np.uint8)
+        self.level_data = [
+            PyramidLevel(sh["block_size"][l], sh["search_size"][l], float(sh["block_size"][l] // 2), sh["level_width"][l],
+                         sh["level_height"][l]) for l in range(num_levels)
+        ]
+
+    def calcMotionBlockMatching(self):
+        return self._est.estimate(self._im1, self._im2)
+
+    def stats(self):
+        return self._est.stats()
+
+    def close(self):
+        self._est.close()
+
+
+class Flow:
+    """Mirror of `class Flow` (rw_flow.h:9-38) for the parts on the path: .flo codec and the AEE metric."""
+
+    def __init__(self):
+        self._lib = _lib.load()
+
+    def ReadFlowFile(self, filename):
+        if filename is None:
+            raise BbmeError(-1, "ReadFlowFile: empty filename")
+        w, h = C.c_int(0), C.c_int(0)
+        rc = self._lib.bbme_flo_read_header(str(filename).encode(), C.byref(w), C.byref(h))
+        if rc != 0:
+            raise BbmeError(rc, "ReadFlowFile: " + self._lib.bbme_status_string(rc).decode())
+        img = np.empty((h.value, w.value, 2), np.float32)
+        rc = self._lib.bbme_flo_read(str(filename).encode(), img.ctypes.data, w.value, h.value)
+        if rc != 0:
+            raise BbmeError(rc, "ReadFlowFile: " + self._lib.bbme_status_string(rc).decode())
+        return img
+
+    def WriteFlowFile(self, img, filename):
+        if filename is None:
+            raise BbmeError(-1, "WriteFlowFile: empty filename")
+        img = np.ascontiguousarray(img, np.float32)
+        h, w, _ = img.shape
+        rc = self._lib.bbme_flo_write(str(filename).encode(), img.ctypes.data, w, h)
+        if rc != 0:
+            raise BbmeError(rc, "WriteFlowFile: " + self._lib.bbme_status_string(rc).decode())
+
+    def CalculateMSE(self, gtruth, flow):
+        gt = np.ascontiguousarray(gtruth, np.float32)
+        fl = np.ascontiguousarray(flow, np.float32)
+        h, w, _ = gt.shape
+        return float(self._lib.bbme_flow_aee(gt.ctypes.data, fl.ctypes.data, w, h))
+
+    def StripAndSubsample(self, padded_flow, shape, factor):
+        """main()'s post-processing (main_class.cpp:58-70)."""
+        sh = BbmeShape()
+        for k in ("width", "height", "padded_width", "padded_height", "padding_x", "padding_y", "num_levels"):
+            setattr(sh, k, shape[k])
+        pf = np.ascontiguousarray(padded_flow, np.float32)
+        out = np.empty((shape["height"] // factor, shape["width"] // factor, 2), np.float32)
+        rc = self._lib.bbme_flow_strip_subsample(pf.ctypes.data, C.byref(sh), int(factor), out.ctypes.data)
+        if rc != 0:
+            raise BbmeError(rc, "StripAndSubsample: " + self._lib.bbme_status_string(rc).decode())
+        return out

@@ -1,0 +1,782 @@
+// capi.cu -- the C ABI of libbbme.so (include/bbme.h): context, plan, batched pipeline driver, stage entry points.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/bbme.h"
+#include "kernels.h"
+
+using namespace bbme;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  uint8_t* in1 = nullptr;  // staged host frames: chunk planes of in_pitch x height
+  uint8_t* in2 = nullptr;
+  uint8_t* img[2][kMaxLevels] = {};
+  short2* mv_a[kMaxLevels] = {};
+  short2* mv_b[kMaxLevels] = {};
+  short2* mv_search[kMaxLevels] = {};
+  short2* mv_final[kMaxLevels] = {};
+  uint32_t* list0 = nullptr;
+  uint32_t* list1 = nullptr;
+  short2* nv = nullptr;
+  uint32_t* stamp = nullptr;
+  uint32_t* ctr = nullptr;
+  unsigned long long* counters = nullptr;  // [0] candidates, [1] absdiffs
+  float* out = nullptr;
+  TmaSearchPlan tma[kMaxLevels];
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> ev_tag;
+  int last_n = 0;
+};
+
+enum { TAG_PYR = 0, TAG_SEARCH = 1, TAG_REG = 2, TAG_OTHER = 3 };
+
+}  // namespace
+
+struct bbme_ctx {
+  int device = 0;
+  int sm_count = 0;
+  std::string err;
+  bool planned = false;
+  bbme_shape shape{};
+  bbme_options opt{};
+  int pitch[kMaxLevels] = {};
+  size_t plane[kMaxLevels] = {};
+  size_t cap[kMaxLevels] = {};  // mv entries per pair per level (2x2 granularity)
+  int in_pitch = 0;
+  size_t in_plane = 0;
+  size_t out_plane = 0;  // floats
+  std::vector<Slot> slots;
+  std::vector<void*> allocs;
+  bbme_stats stats{};
+  uint32_t launches = 0;
+};
+
+namespace {
+
+int fail(bbme_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  else g_create_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(c, expr)                                                                                    \
+  do {                                                                                                       \
+    cudaError_t e_ = (expr);                                                                                 \
+    if (e_ != cudaSuccess) return fail((c), BBME_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                                       __FILE__, __LINE__);                                                  \
+  } while (0)
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+template <typename T>
+int dev_alloc(bbme_ctx* c, T** p, size_t count, bool zero) {
+  void* q = nullptr;
+  size_t bytes = count * sizeof(T) + 256;  // slack: kernels may read a few bytes past the last row
+  cudaError_t e = cudaMalloc(&q, bytes);
+  if (e != cudaSuccess) return fail(c, BBME_E_NOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+  if (zero) {
+    e = cudaMemset(q, 0, bytes);
+    if (e != cudaSuccess) return fail(c, BBME_E_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+  }
+  c->allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return BBME_OK;
+}
+
+void release_plan(bbme_ctx* c) {
+  for (Slot& s : c->slots) {
+    for (cudaEvent_t e : s.ev) cudaEventDestroy(e);
+    if (s.stream) cudaStreamDestroy(s.stream);
+  }
+  c->slots.clear();
+  for (void* p : c->allocs) cudaFree(p);
+  c->allocs.clear();
+  c->planned = false;
+}
+
+int shape_status(int w, int h, int levels, const int* ss, const int* bs, bbme_shape* out) {
+  if (w <= 0 || h <= 0 || levels <= 0 || levels > BBME_MAX_LEVELS || !bs || !ss || !out) return BBME_E_ARG;
+  for (int i = 0; i < levels; ++i)
+    if (!is_pow2(bs[i]) || bs[i] < 2 || bs[i] > 128 || ss[i] <= 0) return BBME_E_ARG;
+  // Padding search of MF::MF (motion_framework.cpp:15-46): smallest Hp >= H, Wp >= W divisible by 2^i * bs[i]
+  // for every level, each axis bumped independently; the reference aborts when either axis reaches twice the
+  // original, and tests that BEFORE testing divisibility (:21-26).
+  long long th = h, tw = w;
+  for (;;) {
+    if (th == 2LL * h || tw == 2LL * w) return BBME_E_NOPAD;
+    bool okh = true, okw = true;
+    for (int i = 0; i < levels; ++i) {
+      const long long q = (1LL << i) * bs[i];
+      okh = okh && (th % q == 0);
+      okw = okw && (tw % q == 0);
+    }
+    if (okh && okw) break;
+    if (!okh) ++th;
+    if (!okw) ++tw;
+  }
+  memset(out, 0, sizeof(*out));
+  out->width = w;
+  out->height = h;
+  out->padded_width = (int)tw;
+  out->padded_height = (int)th;
+  out->padding_x = ((int)tw - w) / 2;
+  out->padding_y = ((int)th - h) / 2;
+  out->num_levels = levels;
+  if (w + 2 * out->padding_x != out->padded_width || h + 2 * out->padding_y != out->padded_height) return BBME_E_ODD_PAD;
+  int lw = out->padded_width, lh = out->padded_height;
+  for (int i = 0; i < levels; ++i) {
+    out->level_width[i] = lw;
+    out->level_height[i] = lh;
+    out->block_size[i] = bs[i];
+    out->search_size[i] = ss[i];
+    if (lw / bs[i] < 2 || lh / bs[i] < 2) return BBME_E_ONE_BLOCK;
+    lw /= 2;
+    lh /= 2;
+  }
+  if (out->padded_width > 16383 || out->padded_height > 16383) return BBME_E_RANGE;
+  return BBME_OK;
+}
+
+int radius_of(int ss, int bs) {
+  const int shift = ss - bs;
+  return shift > 0 ? (shift >> 1) : 0;  // spiral covers [-R,R]^2 with R = (ss-bs)>>1 (motion_framework.cpp:299,326-411)
+}
+
+void mark(bbme_ctx* c, Slot& s, int tag) {
+  if (!c->opt.collect_stats) return;
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, s.stream);
+  s.ev.push_back(e);
+  s.ev_tag.push_back(tag);
+}
+
+void fold_events(bbme_ctx* c, Slot& s) {
+  if (s.ev.size() >= 2) {
+    for (size_t i = 1; i < s.ev.size(); ++i) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, s.ev[i - 1], s.ev[i]) != cudaSuccess) continue;
+      switch (s.ev_tag[i]) {
+        case TAG_PYR: c->stats.ms_pyramid += ms; break;
+        case TAG_SEARCH: c->stats.ms_search += ms; break;
+        case TAG_REG: c->stats.ms_regularize += ms; break;
+        default: c->stats.ms_other += ms; break;
+      }
+      c->stats.ms_total += ms;
+    }
+  }
+  for (cudaEvent_t e : s.ev) cudaEventDestroy(e);
+  s.ev.clear();
+  s.ev_tag.clear();
+}
+
+// The device pipeline for n pairs resident in slot `s` input planes (d_in1/d_in2), enqueued on s.stream.
+int run_chunk(bbme_ctx* c, Slot& s, int n, const uint8_t* d_in1, const uint8_t* d_in2, size_t in_pitch,
+              size_t in_plane, float* d_flow, size_t flow_plane, int16_t* d_compact, size_t compact_plane) {
+  const bbme_shape& sh = c->shape;
+  const int L = sh.num_levels;
+  cudaStream_t st = s.stream;
+  s.last_n = n;
+  if (c->opt.collect_stats) {
+    cudaMemsetAsync(s.counters, 0, 2 * sizeof(unsigned long long), st);
+    cudaMemset2DAsync(s.ctr + CTR_ROUNDS, kCtrWords * sizeof(uint32_t), 0, 2 * sizeof(uint32_t), n, st);
+  }
+  mark(c, s, TAG_OTHER);
+  // ---- MF::MF: pad + Gaussian pyramid (motion_framework.cpp:57-106)
+  launch_pad(d_in1, d_in2, in_pitch, in_plane, sh.width, sh.height, sh.padding_x, sh.padding_y, s.img[0][0],
+             s.img[1][0], c->pitch[0], c->plane[0], sh.padded_width, sh.padded_height, n, st);
+  ++c->launches;
+  for (int l = 1; l < L; ++l) {
+    ImgView a{s.img[0][l - 1], sh.level_width[l - 1], sh.level_height[l - 1], c->pitch[l - 1], c->plane[l - 1]};
+    ImgView b{s.img[1][l - 1], sh.level_width[l - 1], sh.level_height[l - 1], c->pitch[l - 1], c->plane[l - 1]};
+    launch_pyrdown(a, b, s.img[0][l], s.img[1][l], c->pitch[l], c->plane[l], n, st);
+    ++c->launches;
+  }
+  mark(c, s, TAG_PYR);
+  // ---- MF::calcMotionBlockMatching: coarse to fine (motion_framework.cpp:113-219)
+  for (int l = L - 1; l >= 0; --l) {
+    const int lw = sh.level_width[l], lh = sh.level_height[l];
+    const int bs0 = sh.block_size[l];
+    const int R = radius_of(sh.search_size[l], bs0);
+    ImgView i1{s.img[0][l], lw, lh, c->pitch[l], c->plane[l]};
+    ImgView i2{s.img[1][l], lw, lh, c->pitch[l], c->plane[l]};
+    short2* cur = s.mv_a[l];
+    short2* nxt = s.mv_b[l];
+    int g = bs0, gw = lw / g, gh = lh / g;
+    MvView field{cur, gw, gh, c->cap[l]};
+    if (l == L - 1) {
+      cudaMemsetAsync(cur, 0, (size_t)n * c->cap[l] * sizeof(short2), st);  // level_flow starts at zero (:70,92)
+    } else {
+      launch_copy_mvs(s.mv_final[l + 1], sh.level_width[l + 1] / 2, c->cap[l + 1], sh.block_size[l + 1], field, g, n, st);
+      ++c->launches;
+    }
+    mark(c, s, TAG_OTHER);
+    const bool use_tma = s.tma[l].supported && c->opt.search_kernel != 1;
+    unsigned long long* ctrs = c->opt.collect_stats ? s.counters : nullptr;
+    if (use_tma) launch_search_tma(s.tma[l], i1, i2, field, n, ctrs, c->sm_count, st);
+    else launch_search_generic(i1, i2, field, g, R, n, ctrs, st);
+    ++c->launches;
+    mark(c, s, TAG_SEARCH);
+    if (c->opt.keep_search_mv && s.mv_search[l]) {
+      cudaMemcpy2DAsync(s.mv_search[l], (size_t)gw * gh * sizeof(short2), cur, c->cap[l] * sizeof(short2),
+                        (size_t)gw * gh * sizeof(short2), n, cudaMemcpyDeviceToDevice, st);
+    }
+    // regularisation schedule (motion_framework.cpp:133-154): per block size `sweeps` sweeps with
+    // lambda_multiplier 1..sweeps, then split; lambda starts at bs/2 (integer division, :73,95) and doubles.
+    float lambda = (float)(bs0 / 2);
+    while (g > 1) {
+      for (int sw = 1; sw <= c->opt.sweeps; ++sw) {
+        RegArgs ra;
+        ra.i1 = i1;
+        ra.i2 = i2;
+        ra.bs = g;
+        ra.gw = gw;
+        ra.gh = gh;
+        ra.lm = lambda * (float)sw;
+        ra.O = cur;
+        ra.Y = nxt;
+        ra.mv_plane = c->cap[l];
+        ra.list0 = s.list0;
+        ra.list1 = s.list1;
+        ra.nv = s.nv;
+        ra.stamp = s.stamp;
+        ra.wl_plane = c->cap[0];
+        ra.ctr = s.ctr;
+        launch_reg_full(ra, n, st);
+        launch_reg_fix(ra, n, st);
+        c->launches += 2;
+        short2* t = cur; cur = nxt; nxt = t;
+      }
+      if (g > 2) {
+        launch_divide(cur, gw, gh, c->cap[l], nxt, c->cap[l], n, st);
+        ++c->launches;
+        short2* t = cur; cur = nxt; nxt = t;
+        gw *= 2;
+        gh *= 2;
+      }
+      g >>= 1;
+      lambda = lambda * 2;
+    }
+    s.mv_final[l] = cur;
+    mark(c, s, TAG_REG);
+  }
+  // ---- final dense field (motion_framework.cpp:205-206,218)
+  if (d_flow) {
+    launch_export(s.mv_final[0], sh.padded_width / 2, c->cap[0], d_flow, sh.padded_width, sh.padded_height, flow_plane, n, st);
+    ++c->launches;
+  }
+  if (d_compact) {
+    launch_export_compact(s.mv_final[0], sh.padded_width / 2, sh.padded_height / 2, c->cap[0], d_compact, compact_plane, n, st);
+    ++c->launches;
+  }
+  mark(c, s, TAG_OTHER);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(c, BBME_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return BBME_OK;
+}
+
+int collect_after_sync(bbme_ctx* c) {
+  if (!c->opt.collect_stats) return BBME_OK;
+  for (Slot& s : c->slots) {
+    fold_events(c, s);
+    if (s.last_n > 0) {
+      unsigned long long h[2] = {0, 0};
+      CUDA_TRY(c, cudaMemcpy(h, s.counters, sizeof(h), cudaMemcpyDeviceToHost));
+      c->stats.search_candidates += h[0];
+      c->stats.search_absdiffs += h[1];
+      std::vector<uint32_t> ctr((size_t)s.last_n * kCtrWords);
+      CUDA_TRY(c, cudaMemcpy(ctr.data(), s.ctr, ctr.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      for (int p = 0; p < s.last_n; ++p) {
+        c->stats.fix_rounds += ctr[(size_t)p * kCtrWords + CTR_ROUNDS];
+        c->stats.fix_blocks += ctr[(size_t)p * kCtrWords + CTR_BLOCKS];
+      }
+      s.last_n = 0;
+    }
+  }
+  return BBME_OK;
+}
+
+int sync_all(bbme_ctx* c) {
+  for (Slot& s : c->slots) CUDA_TRY(c, cudaStreamSynchronize(s.stream));
+  return BBME_OK;
+}
+
+void begin_call(bbme_ctx* c) {
+  memset(&c->stats, 0, sizeof(c->stats));
+  c->launches = 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+void bbme_default_options(bbme_options* o) {
+  if (!o) return;
+  o->sweeps = 2;
+  o->chunk_pairs = 1;
+  o->slots = 1;
+  o->search_kernel = 0;
+  o->collect_stats = 0;
+  o->keep_search_mv = 0;
+}
+
+int bbme_version(void) { return BBME_VERSION; }
+
+const char* bbme_status_string(int s) {
+  switch (s) {
+    case BBME_OK: return "ok";
+    case BBME_E_ARG: return "invalid argument";
+    case BBME_E_NOPAD: return "Could not find any multiples of the block size that match padded image dimensions";
+    case BBME_E_ODD_PAD: return "padded size minus original size is odd (unsupported: the reference reads out of bounds)";
+    case BBME_E_ONE_BLOCK: return "fewer than two blocks along an axis at some level (unsupported: the reference reads out of bounds)";
+    case BBME_E_NOMEM: return "out of memory";
+    case BBME_E_CUDA: return "CUDA error";
+    case BBME_E_STATE: return "invalid call order or size for this plan";
+    case BBME_E_IO: return "file I/O error";
+    case BBME_E_FORMAT: return "bad .flo file";
+    case BBME_E_RANGE: return "image too large for int16 motion vectors";
+    default: return "unknown status";
+  }
+}
+
+int bbme_plan_shape(int width, int height, int num_levels, const int* search_size, const int* block_size,
+                    bbme_shape* out) {
+  return shape_status(width, height, num_levels, search_size, block_size, out);
+}
+
+int bbme_create(bbme_ctx** out, int device) {
+  if (!out) return fail(nullptr, BBME_E_ARG, "bbme_create: null output pointer");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(nullptr, BBME_E_CUDA, "no usable CUDA device (%s); this library has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  if (device < 0 || device >= count) return fail(nullptr, BBME_E_ARG, "device %d out of range (0..%d)", device, count - 1);
+  cudaDeviceProp prop;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+    return fail(nullptr, BBME_E_CUDA, "cannot select device %d: %s", device, cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, BBME_E_CUDA, "device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major,
+                prop.minor);
+  bbme_ctx* c = new bbme_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  bbme_default_options(&c->opt);
+  *out = c;
+  return BBME_OK;
+}
+
+void bbme_destroy(bbme_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  release_plan(c);
+  delete c;
+}
+
+const char* bbme_last_error(const bbme_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int bbme_plan(bbme_ctx* c, int width, int height, int num_levels, const int* search_size, const int* block_size,
+              const bbme_options* opt, bbme_shape* out) {
+  if (!c) return BBME_E_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  release_plan(c);
+  bbme_shape sh;
+  int rc = shape_status(width, height, num_levels, search_size, block_size, &sh);
+  if (rc != BBME_OK) return fail(c, rc, "bbme_plan(%dx%d, %d levels): %s", width, height, num_levels, bbme_status_string(rc));
+  bbme_options o;
+  bbme_default_options(&o);
+  if (opt) o = *opt;
+  if (o.sweeps < 0 || o.chunk_pairs < 1 || o.slots < 1 || o.slots > 4 || o.search_kernel < 0 || o.search_kernel > 2)
+    return fail(c, BBME_E_ARG, "bbme_plan: bad options (sweeps=%d chunk_pairs=%d slots=%d search_kernel=%d)", o.sweeps,
+                o.chunk_pairs, o.slots, o.search_kernel);
+  c->shape = sh;
+  c->opt = o;
+  const int L = sh.num_levels;
+  for (int l = 0; l < L; ++l) {
+    c->pitch[l] = round_up(sh.level_width[l] + 4, 64);
+    c->plane[l] = (size_t)c->pitch[l] * sh.level_height[l];
+    c->cap[l] = (size_t)(sh.level_width[l] / 2) * (sh.level_height[l] / 2);
+  }
+  c->in_pitch = round_up(width, 16);
+  c->in_plane = (size_t)c->in_pitch * height;
+  c->out_plane = (size_t)sh.padded_width * sh.padded_height * 2;
+  const size_t n = (size_t)o.chunk_pairs;
+  c->slots.resize(o.slots);
+  for (Slot& s : c->slots) {
+    CUDA_TRY(c, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    if ((rc = dev_alloc(c, &s.in1, n * c->in_plane, false)) || (rc = dev_alloc(c, &s.in2, n * c->in_plane, false))) return rc;
+    for (int l = 0; l < L; ++l) {
+      for (int f = 0; f < 2; ++f)
+        if ((rc = dev_alloc(c, &s.img[f][l], n * c->plane[l], true))) return rc;
+      if ((rc = dev_alloc(c, &s.mv_a[l], n * c->cap[l], true)) || (rc = dev_alloc(c, &s.mv_b[l], n * c->cap[l], true))) return rc;
+      if (o.keep_search_mv) {
+        const size_t blocks = (size_t)(sh.level_width[l] / sh.block_size[l]) * (sh.level_height[l] / sh.block_size[l]);
+        if ((rc = dev_alloc(c, &s.mv_search[l], n * blocks, true))) return rc;
+      }
+      s.mv_final[l] = s.mv_a[l];
+    }
+    if ((rc = dev_alloc(c, &s.list0, n * c->cap[0], false)) || (rc = dev_alloc(c, &s.list1, n * c->cap[0], false)) ||
+        (rc = dev_alloc(c, &s.nv, n * c->cap[0], false)) || (rc = dev_alloc(c, &s.stamp, n * c->cap[0], true)) ||
+        (rc = dev_alloc(c, &s.ctr, n * kCtrWords, true)) || (rc = dev_alloc(c, &s.counters, (size_t)2, true)) ||
+        (rc = dev_alloc(c, &s.out, n * c->out_plane, false)))
+      return rc;
+    for (int l = 0; l < L; ++l) {
+      memset(&s.tma[l], 0, sizeof(s.tma[l]));
+      if (o.search_kernel == 1) continue;
+      char msg[256] = {0};
+      const int R = radius_of(sh.search_size[l], sh.block_size[l]);
+      int trc = tma_search_plan(&s.tma[l], s.img[0][l], s.img[1][l], sh.level_width[l], sh.level_height[l], c->pitch[l],
+                                c->plane[l], o.chunk_pairs, sh.block_size[l], R, msg, sizeof(msg));
+      if (trc != 0) return fail(c, BBME_E_CUDA, "TMA search plan failed at level %d: %s", l, msg);
+      if (o.search_kernel == 2 && !s.tma[l].supported)
+        return fail(c, BBME_E_ARG, "search_kernel=2 but level %d (block %d, R %d) is not covered by the TMA kernel", l,
+                    sh.block_size[l], R);
+    }
+  }
+  c->planned = true;
+  if (out) *out = sh;
+  return BBME_OK;
+}
+
+int bbme_get_shape(const bbme_ctx* c, bbme_shape* out) {
+  if (!c || !out) return BBME_E_ARG;
+  if (!c->planned) return BBME_E_STATE;
+  *out = c->shape;
+  return BBME_OK;
+}
+
+int bbme_sync(bbme_ctx* c) {
+  if (!c) return BBME_E_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  int rc = sync_all(c);
+  if (rc) return rc;
+  return collect_after_sync(c);
+}
+
+int bbme_get_stats(bbme_ctx* c, bbme_stats* out) {
+  if (!c || !out) return BBME_E_ARG;
+  *out = c->stats;
+  out->kernel_launches = c->launches;
+  return BBME_OK;
+}
+
+int bbme_estimate_batch(bbme_ctx* c, int n, const uint8_t* const* im1, const uint8_t* const* im2, size_t pitch,
+                        float* const* flow) {
+  if (!c) return BBME_E_ARG;
+  if (!c->planned) return fail(c, BBME_E_STATE, "bbme_estimate_batch before bbme_plan");
+  if (n <= 0 || !im1 || !im2 || !flow || pitch < (size_t)c->shape.width) return fail(c, BBME_E_ARG, "bbme_estimate_batch: bad arguments");
+  for (int i = 0; i < n; ++i)
+    if (!im1[i] || !im2[i] || !flow[i]) return fail(c, BBME_E_ARG, "bbme_estimate_batch: null buffer for pair %d", i);
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  begin_call(c);
+  const int chunk = c->opt.chunk_pairs;
+  const size_t flow_bytes = c->out_plane * sizeof(float);
+  int ci = 0;
+  for (int start = 0; start < n; start += chunk, ++ci) {
+    Slot& s = c->slots[ci % c->slots.size()];
+    const int m = (n - start < chunk) ? (n - start) : chunk;
+    if (c->opt.collect_stats && ci >= (int)c->slots.size()) {  // slot reuse: fold its previous chunk first
+      CUDA_TRY(c, cudaStreamSynchronize(s.stream));
+      int rc0 = collect_after_sync(c);
+      if (rc0) return rc0;
+    }
+    for (int i = 0; i < m; ++i) {
+      CUDA_TRY(c, cudaMemcpy2DAsync(s.in1 + (size_t)i * c->in_plane, c->in_pitch, im1[start + i], pitch, c->shape.width,
+                                    c->shape.height, cudaMemcpyHostToDevice, s.stream));
+      CUDA_TRY(c, cudaMemcpy2DAsync(s.in2 + (size_t)i * c->in_plane, c->in_pitch, im2[start + i], pitch, c->shape.width,
+                                    c->shape.height, cudaMemcpyHostToDevice, s.stream));
+    }
+    int rc = run_chunk(c, s, m, s.in1, s.in2, c->in_pitch, c->in_plane, s.out, c->out_plane, nullptr, 0);
+    if (rc) return rc;
+    for (int i = 0; i < m; ++i)
+      CUDA_TRY(c, cudaMemcpyAsync(flow[start + i], s.out + (size_t)i * c->out_plane, flow_bytes, cudaMemcpyDeviceToHost, s.stream));
+  }
+  int rc = sync_all(c);
+  if (rc) return rc;
+  return collect_after_sync(c);
+}
+
+int bbme_estimate(bbme_ctx* c, const uint8_t* im1, const uint8_t* im2, size_t pitch, float* flow) {
+  return bbme_estimate_batch(c, 1, &im1, &im2, pitch, &flow);
+}
+
+static int estimate_device_impl(bbme_ctx* c, int n, const uint8_t* d1, const uint8_t* d2, size_t pitch, size_t plane,
+                                float* d_flow, size_t flow_plane, int16_t* d_mv, size_t mv_plane) {
+  if (!c) return BBME_E_ARG;
+  if (!c->planned) return fail(c, BBME_E_STATE, "bbme_estimate_device before bbme_plan");
+  if (n <= 0 || !d1 || !d2 || pitch < (size_t)c->shape.width || plane < pitch * (size_t)c->shape.height)
+    return fail(c, BBME_E_ARG, "bbme_estimate_device: bad arguments");
+  if (d_flow && flow_plane < c->out_plane) return fail(c, BBME_E_ARG, "bbme_estimate_device: flow plane stride too small");
+  if (d_mv && mv_plane < c->cap[0] * 2) return fail(c, BBME_E_ARG, "bbme_estimate_device: mv plane stride too small");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  begin_call(c);
+  const int chunk = c->opt.chunk_pairs;
+  int ci = 0;
+  for (int start = 0; start < n; start += chunk, ++ci) {
+    Slot& s = c->slots[ci % c->slots.size()];
+    const int m = (n - start < chunk) ? (n - start) : chunk;
+    if (c->opt.collect_stats && ci >= (int)c->slots.size()) {
+      CUDA_TRY(c, cudaStreamSynchronize(s.stream));
+      int rc0 = collect_after_sync(c);
+      if (rc0) return rc0;
+    }
+    int rc = run_chunk(c, s, m, d1 + (size_t)start * plane, d2 + (size_t)start * plane, pitch, plane,
+                       d_flow ? d_flow + (size_t)start * flow_plane : nullptr, flow_plane,
+                       d_mv ? d_mv + (size_t)start * mv_plane : nullptr, mv_plane);
+    if (rc) return rc;
+  }
+  return BBME_OK;
+}
+
+int bbme_estimate_device(bbme_ctx* c, int n, const uint8_t* d1, const uint8_t* d2, size_t pitch, size_t plane,
+                         float* d_flow, size_t flow_plane) {
+  if (!d_flow) return c ? fail(c, BBME_E_ARG, "bbme_estimate_device: null flow") : BBME_E_ARG;
+  return estimate_device_impl(c, n, d1, d2, pitch, plane, d_flow, flow_plane, nullptr, 0);
+}
+
+int bbme_estimate_device_compact(bbme_ctx* c, int n, const uint8_t* d1, const uint8_t* d2, size_t pitch, size_t plane,
+                                 int16_t* d_mv, size_t mv_plane) {
+  if (!d_mv) return c ? fail(c, BBME_E_ARG, "bbme_estimate_device_compact: null mv") : BBME_E_ARG;
+  return estimate_device_impl(c, n, d1, d2, pitch, plane, nullptr, 0, d_mv, mv_plane);
+}
+
+int bbme_host_alloc(void** p, size_t bytes) {
+  if (!p) return BBME_E_ARG;
+  return cudaHostAlloc(p, bytes, cudaHostAllocDefault) == cudaSuccess ? BBME_OK : BBME_E_NOMEM;
+}
+
+void bbme_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+// ------------------------------------------------------------------------------------------------ debug state
+
+int bbme_debug_level_image(bbme_ctx* c, int pair, int frame, int level, uint8_t* out) {
+  if (!c || !out) return BBME_E_ARG;
+  if (!c->planned) return BBME_E_STATE;
+  if (pair < 0 || pair >= c->opt.chunk_pairs || frame < 0 || frame > 1 || level < 0 || level >= c->shape.num_levels)
+    return fail(c, BBME_E_ARG, "bbme_debug_level_image: index out of range");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  Slot& s = c->slots[0];
+  CUDA_TRY(c, cudaStreamSynchronize(s.stream));
+  const int w = c->shape.level_width[level], h = c->shape.level_height[level];
+  CUDA_TRY(c, cudaMemcpy2D(out, w, s.img[frame][level] + (size_t)pair * c->plane[level], c->pitch[level], w, h,
+                           cudaMemcpyDeviceToHost));
+  return BBME_OK;
+}
+
+int bbme_debug_level_mv(bbme_ctx* c, int pair, int level, int which, int16_t* out) {
+  if (!c || !out) return BBME_E_ARG;
+  if (!c->planned) return BBME_E_STATE;
+  if (pair < 0 || pair >= c->opt.chunk_pairs || level < 0 || level >= c->shape.num_levels || which < 0 || which > 1)
+    return fail(c, BBME_E_ARG, "bbme_debug_level_mv: index out of range");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  Slot& s = c->slots[0];
+  CUDA_TRY(c, cudaStreamSynchronize(s.stream));
+  const int w = c->shape.level_width[level], h = c->shape.level_height[level];
+  if (which == 0) {
+    CUDA_TRY(c, cudaMemcpy(out, s.mv_final[level] + (size_t)pair * c->cap[level], c->cap[level] * sizeof(short2),
+                           cudaMemcpyDeviceToHost));
+  } else {
+    if (!s.mv_search[level]) return fail(c, BBME_E_STATE, "plan was made without keep_search_mv");
+    const int bs = c->shape.block_size[level];
+    const size_t blocks = (size_t)(w / bs) * (h / bs);
+    CUDA_TRY(c, cudaMemcpy(out, s.mv_search[level] + (size_t)pair * blocks, blocks * sizeof(short2), cudaMemcpyDeviceToHost));
+  }
+  return BBME_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ single stages
+
+}  // extern "C"
+
+namespace {
+struct Scratch {
+  std::vector<void*> p;
+  ~Scratch() {
+    for (void* q : p) cudaFree(q);
+  }
+  template <typename T>
+  T* get(size_t count, bool zero) {
+    void* q = nullptr;
+    if (cudaMalloc(&q, count * sizeof(T) + 256) != cudaSuccess) return nullptr;
+    if (zero) cudaMemset(q, 0, count * sizeof(T) + 256);
+    p.push_back(q);
+    return reinterpret_cast<T*>(q);
+  }
+};
+
+int upload_image(bbme_ctx* c, Scratch& sc, const uint8_t* host, int w, int h, int* pitch_out, uint8_t** dev) {
+  const int pitch = round_up(w + 4, 64);
+  uint8_t* d = sc.get<uint8_t>((size_t)pitch * h, true);
+  if (!d) return fail(c, BBME_E_NOMEM, "stage: cudaMalloc failed");
+  CUDA_TRY(c, cudaMemcpy2D(d, pitch, host, w, w, h, cudaMemcpyHostToDevice));
+  *pitch_out = pitch;
+  *dev = d;
+  return BBME_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int bbme_stage_pyrdown(bbme_ctx* c, const uint8_t* src, int w, int h, uint8_t* dst) {
+  if (!c || !src || !dst || w < 2 || h < 2) return BBME_E_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  Scratch sc;
+  int sp = 0, rc;
+  uint8_t* ds = nullptr;
+  if ((rc = upload_image(c, sc, src, w, h, &sp, &ds))) return rc;
+  const int dw = w / 2, dh = h / 2, dp = round_up(dw + 4, 64);
+  uint8_t* dd = sc.get<uint8_t>((size_t)dp * dh * 2, true);
+  if (!dd) return fail(c, BBME_E_NOMEM, "stage: cudaMalloc failed");
+  ImgView v{ds, w, h, sp, (size_t)sp * h};
+  launch_pyrdown(v, v, dd, dd + (size_t)dp * dh, dp, 0, 1, 0);
+  CUDA_TRY(c, cudaDeviceSynchronize());
+  CUDA_TRY(c, cudaMemcpy2D(dst, dw, dd, dp, dw, dh, cudaMemcpyDeviceToHost));
+  return BBME_OK;
+}
+
+int bbme_stage_search(bbme_ctx* c, const uint8_t* im1, const uint8_t* im2, int w, int h, int bs, int ss, int16_t* mv,
+                      int kernel, bbme_stats* st) {
+  if (!c || !im1 || !im2 || !mv || !is_pow2(bs) || bs < 2 || w % bs || h % bs) return BBME_E_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  Scratch sc;
+  int pitch = 0, rc;
+  uint8_t *d1 = nullptr, *d2 = nullptr;
+  if ((rc = upload_image(c, sc, im1, w, h, &pitch, &d1)) || (rc = upload_image(c, sc, im2, w, h, &pitch, &d2))) return rc;
+  const int gw = w / bs, gh = h / bs, R = radius_of(ss, bs);
+  short2* dmv = sc.get<short2>((size_t)gw * gh, false);
+  unsigned long long* ctr = sc.get<unsigned long long>(2, true);
+  if (!dmv || !ctr) return fail(c, BBME_E_NOMEM, "stage: cudaMalloc failed");
+  CUDA_TRY(c, cudaMemcpy(dmv, mv, (size_t)gw * gh * sizeof(short2), cudaMemcpyHostToDevice));
+  ImgView i1{d1, w, h, pitch, (size_t)pitch * h}, i2{d2, w, h, pitch, (size_t)pitch * h};
+  MvView f{dmv, gw, gh, (size_t)gw * gh};
+  TmaSearchPlan plan;
+  memset(&plan, 0, sizeof(plan));
+  if (kernel != 1) {
+    char msg[256] = {0};
+    if (tma_search_plan(&plan, d1, d2, w, h, pitch, (size_t)pitch * h, 1, bs, R, msg, sizeof(msg)) != 0)
+      return fail(c, BBME_E_CUDA, "stage_search: %s", msg);
+    if (kernel == 2 && !plan.supported) return fail(c, BBME_E_ARG, "stage_search: (block %d, R %d) not covered by the TMA kernel", bs, R);
+  }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0, 0);
+  if (plan.supported) launch_search_tma(plan, i1, i2, f, 1, ctr, c->sm_count, 0);
+  else launch_search_generic(i1, i2, f, bs, R, 1, ctr, 0);
+  cudaEventRecord(e1, 0);
+  cudaError_t e = cudaDeviceSynchronize();
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (e != cudaSuccess) return fail(c, BBME_E_CUDA, "stage_search kernel failed: %s", cudaGetErrorString(e));
+  CUDA_TRY(c, cudaMemcpy(mv, dmv, (size_t)gw * gh * sizeof(short2), cudaMemcpyDeviceToHost));
+  if (st) {
+    memset(st, 0, sizeof(*st));
+    unsigned long long hc[2];
+    CUDA_TRY(c, cudaMemcpy(hc, ctr, sizeof(hc), cudaMemcpyDeviceToHost));
+    st->ms_search = ms;
+    st->ms_total = ms;
+    st->kernel_launches = 1;
+    st->search_candidates = hc[0];
+    st->search_absdiffs = hc[1];
+    st->reserved = plan.supported ? 2u : 1u;
+  }
+  return BBME_OK;
+}
+
+int bbme_stage_regularize(bbme_ctx* c, const uint8_t* im1, const uint8_t* im2, int w, int h, int bs, float lambda,
+                          int mult, int16_t* mv, uint32_t* rounds_out) {
+  if (!c || !im1 || !im2 || !mv || !is_pow2(bs) || bs < 2 || w % bs || h % bs || w / bs < 2 || h / bs < 2) return BBME_E_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  Scratch sc;
+  int pitch = 0, rc;
+  uint8_t *d1 = nullptr, *d2 = nullptr;
+  if ((rc = upload_image(c, sc, im1, w, h, &pitch, &d1)) || (rc = upload_image(c, sc, im2, w, h, &pitch, &d2))) return rc;
+  const int gw = w / bs, gh = h / bs;
+  const size_t nb = (size_t)gw * gh;
+  short2* O = sc.get<short2>(nb, false);
+  short2* Y = sc.get<short2>(nb, false);
+  uint32_t* l0 = sc.get<uint32_t>(nb, false);
+  uint32_t* l1 = sc.get<uint32_t>(nb, false);
+  short2* nv = sc.get<short2>(nb, false);
+  uint32_t* stamp = sc.get<uint32_t>(nb, true);
+  uint32_t* ctr = sc.get<uint32_t>(kCtrWords, true);
+  if (!O || !Y || !l0 || !l1 || !nv || !stamp || !ctr) return fail(c, BBME_E_NOMEM, "stage: cudaMalloc failed");
+  CUDA_TRY(c, cudaMemcpy(O, mv, nb * sizeof(short2), cudaMemcpyHostToDevice));
+  RegArgs ra;
+  ra.i1 = ImgView{d1, w, h, pitch, (size_t)pitch * h};
+  ra.i2 = ImgView{d2, w, h, pitch, (size_t)pitch * h};
+  ra.bs = bs; ra.gw = gw; ra.gh = gh;
+  ra.lm = lambda * (float)mult;
+  ra.O = O; ra.Y = Y; ra.mv_plane = nb;
+  ra.list0 = l0; ra.list1 = l1; ra.nv = nv; ra.stamp = stamp; ra.wl_plane = nb; ra.ctr = ctr;
+  launch_reg_full(ra, 1, 0);
+  launch_reg_fix(ra, 1, 0);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return fail(c, BBME_E_CUDA, "stage_regularize kernel failed: %s", cudaGetErrorString(e));
+  CUDA_TRY(c, cudaMemcpy(mv, Y, nb * sizeof(short2), cudaMemcpyDeviceToHost));
+  if (rounds_out) {
+    uint32_t hc[kCtrWords];
+    CUDA_TRY(c, cudaMemcpy(hc, ctr, sizeof(hc), cudaMemcpyDeviceToHost));
+    *rounds_out = hc[CTR_ROUNDS];
+  }
+  return BBME_OK;
+}
+
+int bbme_stage_divide(bbme_ctx* c, const int16_t* mv_in, int gw, int gh, int16_t* mv_out) {
+  if (!c || !mv_in || !mv_out || gw < 1 || gh < 1) return BBME_E_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  Scratch sc;
+  const size_t nb = (size_t)gw * gh;
+  short2* a = sc.get<short2>(nb, false);
+  short2* b = sc.get<short2>(nb * 4, false);
+  if (!a || !b) return fail(c, BBME_E_NOMEM, "stage: cudaMalloc failed");
+  CUDA_TRY(c, cudaMemcpy(a, mv_in, nb * sizeof(short2), cudaMemcpyHostToDevice));
+  launch_divide(a, gw, gh, nb, b, nb * 4, 1, 0);
+  CUDA_TRY(c, cudaDeviceSynchronize());
+  CUDA_TRY(c, cudaMemcpy(mv_out, b, nb * 4 * sizeof(short2), cudaMemcpyDeviceToHost));
+  return BBME_OK;
+}
+
+int bbme_stage_copy_mvs(bbme_ctx* c, const int16_t* coarse_mv, int cw, int ch, int cbs, int fbs, int16_t* fine_pred) {
+  if (!c || !coarse_mv || !fine_pred || !is_pow2(cbs) || !is_pow2(fbs) || cbs < 2 || fbs < 2 || cw % cbs || ch % cbs ||
+      (2 * cw) % fbs || (2 * ch) % fbs)
+    return BBME_E_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  Scratch sc;
+  const size_t nc = (size_t)(cw / 2) * (ch / 2);
+  const int fgw = 2 * cw / fbs, fgh = 2 * ch / fbs;
+  short2* a = sc.get<short2>(nc, false);
+  short2* b = sc.get<short2>((size_t)fgw * fgh, false);
+  if (!a || !b) return fail(c, BBME_E_NOMEM, "stage: cudaMalloc failed");
+  CUDA_TRY(c, cudaMemcpy(a, coarse_mv, nc * sizeof(short2), cudaMemcpyHostToDevice));
+  MvView f{b, fgw, fgh, (size_t)fgw * fgh};
+  launch_copy_mvs(a, cw / 2, nc, cbs, f, fbs, 1, 0);
+  CUDA_TRY(c, cudaDeviceSynchronize());
+  CUDA_TRY(c, cudaMemcpy(fine_pred, b, (size_t)fgw * fgh * sizeof(short2), cudaMemcpyDeviceToHost));
+  return BBME_OK;
+}
+
+}  // extern "C"

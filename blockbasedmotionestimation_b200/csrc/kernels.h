@@ -1,0 +1,76 @@
+// kernels.h -- host-callable launchers of the sm_100a kernels (implemented in kernels.cu / search_tma.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace bbme {
+
+// per-pair control words of the regularisation fix-up (device memory, kCtrWords uint32 per pair)
+constexpr int kCtrWords = 8;
+enum { CTR_COUNT0 = 0, CTR_COUNT1 = 1, CTR_EPOCH = 2, CTR_ROUNDS = 3, CTR_BLOCKS = 4 };
+
+struct RegArgs {
+  ImgView i1, i2;
+  int bs;           // current block size of the stage
+  int gw, gh;       // blocks per row / column at this block size
+  float lm;         // lambda * (float)lambda_multiplier, motion_framework.cpp:607
+  const short2* O;  // field before the sweep ("old")
+  short2* Y;        // field after the sweep
+  size_t mv_plane;  // entries between pairs in O / Y
+  uint32_t* list0;  // work lists, `wl_plane` entries between pairs
+  uint32_t* list1;
+  short2* nv;       // phase-1 results of a fix-up round
+  uint32_t* stamp;  // de-duplication stamps, one per block
+  size_t wl_plane;
+  uint32_t* ctr;    // kCtrWords per pair
+};
+
+// pad (cv::copyMakeBorder constant 0) both frames of n pairs into level 0
+void launch_pad(const uint8_t* in1, const uint8_t* in2, size_t in_pitch, size_t in_plane, int w, int h, int pad_x,
+                int pad_y, uint8_t* out1, uint8_t* out2, int out_pitch, size_t out_plane, int pw, int ph, int n,
+                cudaStream_t s);
+// cv::pyrDown to (sw/2, sh/2), both frames of n pairs
+void launch_pyrdown(ImgView src1, ImgView src2, uint8_t* dst1, uint8_t* dst2, int dpitch, size_t dplane, int n,
+                    cudaStream_t s);
+// generic exhaustive search (any power-of-two block size); mv holds the prediction on entry
+void launch_search_generic(ImgView i1, ImgView i2, MvView mv, int bs, int R, int n, unsigned long long* counters,
+                           cudaStream_t s);
+// MF::copyMVs: coarse final field at 2x2 granularity -> fine prediction at fine block granularity
+void launch_copy_mvs(const short2* coarse, int cgw2, size_t cplane, int cbs, MvView fine, int fbs, int n,
+                     cudaStream_t s);
+// MF::divide_blocks
+void launch_divide(const short2* in, int gw, int gh, size_t in_plane, short2* out, size_t out_plane, int n,
+                   cudaStream_t s);
+// dense CV_32FC2 field from the 2x2-granular level-0 field
+void launch_export(const short2* mv2, int gw2, size_t mv_plane, float* out, int pw, int ph, size_t out_plane, int n,
+                   cudaStream_t s);
+void launch_export_compact(const short2* mv2, int gw2, int gh2, size_t mv_plane, int16_t* out, size_t out_plane, int n,
+                           cudaStream_t s);
+// one regularisation sweep = full Jacobi pass + per-pair fixed-point rounds (exactly the in-place raster result)
+void launch_reg_full(const RegArgs& a, int n, cudaStream_t s);
+void launch_reg_fix(const RegArgs& a, int n, cudaStream_t s);
+
+// ---- TMA search kernel (search_tma.cu)
+struct TmaSearchPlan {
+  int supported;      // 0 if this (bs, R, geometry) is not handled by the TMA kernel
+  int bs, R;
+  int seg;            // candidate rows per thread item
+  int band_rows;      // candidate rows per staged band
+  int box_w, box_h;   // TMA box (bytes, rows)
+  int n_box_x;        // boxes per copy along x
+  int threads;
+  int stages;
+  size_t smem_bytes;
+  CUtensorMap map_win;   // image 2 of this level: dims (w, h, n)
+  CUtensorMap map_blk;   // image 1 of this level
+};
+// returns 0 on success; fills plan->supported
+int tma_search_plan(TmaSearchPlan* plan, const uint8_t* img1, const uint8_t* img2, int w, int h, int pitch,
+                    size_t plane, int n_planes, int bs, int R, char* err, size_t errlen);
+void launch_search_tma(const TmaSearchPlan& plan, ImgView i1, ImgView i2, MvView mv, int n,
+                       unsigned long long* counters, int sm_count, cudaStream_t s);
+
+}  // namespace bbme

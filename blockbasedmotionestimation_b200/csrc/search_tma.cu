@@ -1,0 +1,471 @@
+// search_tma.cu -- exhaustive SAD block search for sm_100a: TMA-staged windows, VABSDIFF4 inner loop.
+//
+// What it computes: MF::calcLevelBM + find_min_block_spiral (reference motion_framework.cpp:226-244,296-422)
+// for every block of every pair of a chunk: all (2R+1)^2 displacements around the predicted position whose
+// block lies inside the image, minimum SAD, ties to the earliest position of the reference's spiral walk.
+//
+// How (B200-first, see DESIGN.md "search kernel"):
+//  * VABSDIFF4.U8.ACC issues at 64 lanes/clk/SM and shares its pipe with SHF/PRMT/LOP3 (bench_micro/int_peak.cu),
+//    so the inner loop must contain nothing but SADs.  The unaligned-window problem (displacement dx shifts the
+//    window by single bytes) is therefore solved by the copy engine, not the ALU: TMA loads FOUR copies of the
+//    search window, shifted by 0..3 bytes, so that every lane reads aligned 32-bit words.
+//  * One warp is the TMA producer (a ring of kStages stages, mbarrier full/empty); eight consumer warps pull
+//    32-lane work items from a shared counter (balances the four SM sub-partitions without CTA barriers).
+//  * A lane owns one displacement column dx and SEG consecutive dy: the 16x16 (or 8x8) block tile lives in 64
+//    (16) registers, SEG accumulators in registers, every window word loaded once per lane feeds up to 16 SADs.
+//  * Copy s is additionally staged `skew*s` rows higher, which rotates its bank mapping by 8 words: the 32 lanes
+//    of a work item (consecutive dx) read 32 distinct banks.
+//  * Block results are reduced with a 64-bit (SAD, spiral rank) key: warp shuffle -> shared atomicMin.
+#include "kernels.h"
+
+#include <stdio.h>
+#include <string.h>
+
+namespace bbme {
+
+constexpr int kStages = 3;
+constexpr int kConsumerWarps = 8;
+constexpr int kThreads = 32 * (1 + kConsumerWarps);
+constexpr int kBlockSlots = kStages + 1;
+
+struct TmaSearchArgs {
+  int w, h;            // level size
+  int gw, gh;          // blocks per row / column
+  int n_pairs;
+  int R, n;            // n = 2R+1
+  int segs_total;      // ceil(n / SEG)
+  int segs_per_band;
+  int nbands;
+  int band_rows;       // segs_per_band * SEG
+  int wi_max;          // 32-lane work items per unit (band)
+  int pww;             // window row pitch in words
+  int copy_words;      // words between shifted copies
+  int skew;            // extra rows per copy index
+  int box_bytes;       // bytes of one window box
+  int blk_bytes;       // bytes of the block box
+  int stage_bytes;
+  short2* mv;
+  size_t mv_plane;
+  unsigned long long* counters;
+};
+
+struct StageMeta {
+  int x2, y2;      // predicted position of the block in image 2
+  int predx, predy;
+  int valid;       // 0: prediction leaves the image -> MV 0, nothing staged (motion_framework.cpp:304-310)
+  int band;
+  int bslot;
+  int gblk;        // global block index (pair * blocks + block)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// inverse of spiral_rank: rank -> (dx, dy)
+__device__ __forceinline__ void spiral_unrank(uint32_t rank, int& dx, int& dy) {
+  dx = 0;
+  dy = 0;
+  if (rank == 0) return;
+  int r = 1;
+  while ((uint32_t)((2 * r + 1) * (2 * r + 1)) <= rank) ++r;
+  const int o = (int)rank - (2 * r - 1) * (2 * r - 1);
+  if (o < 2 * r) { dx = r; dy = o - r + 1; }
+  else if (o < 4 * r) { dy = r; dx = r - 1 - (o - 2 * r); }
+  else if (o < 6 * r) { dx = -r; dy = r - 1 - (o - 4 * r); }
+  else { dy = -r; dx = (o - 6 * r) - r + 1; }
+}
+
+template <int BS, int SEG>
+__global__ void __launch_bounds__(kThreads, 2)
+k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant__ CUtensorMap map_blk,
+             const TmaSearchArgs a) {
+  constexpr int TW = BS >= 16 ? 16 : BS;   // tile width / height held in registers
+  constexpr int TWW = TW / 4;              // tile words per row
+  constexpr int QN = BS / TW;              // tiles per block side
+  constexpr int AP = BS >= 16 ? BS : 16;   // staged block row pitch (TMA inner extent is >= 16 bytes)
+
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t s_full[kStages];
+  __shared__ __align__(8) uint64_t s_empty[kStages];
+  __shared__ StageMeta s_meta[kStages];
+  __shared__ uint32_t s_sdone[kStages];
+  __shared__ unsigned long long s_bkey[kBlockSlots];
+  __shared__ uint32_t s_bdone[kBlockSlots];
+  __shared__ uint32_t s_next;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nblocks = a.gw * a.gh;
+  const int total_blocks = nblocks * a.n_pairs;
+  const int G = gridDim.x, cta = blockIdx.x;
+  const int my_blocks = cta < total_blocks ? (total_blocks - cta + G - 1) / G : 0;
+  const int my_units = my_blocks * a.nbands;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 1);
+      s_sdone[i] = 0;
+    }
+    for (int i = 0; i < kBlockSlots; ++i) {
+      s_bkey[i] = ~0ull;
+      s_bdone[i] = 0;
+    }
+    s_next = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer
+    if (lane == 0) {
+      for (int k = 0; k < my_units; ++k) {
+        const int stage = k % kStages;
+        if (k >= kStages) mbar_wait(&s_empty[stage], (uint32_t)((k / kStages) - 1) & 1u);
+        const int lb = k / a.nbands, band = k - lb * a.nbands;
+        const int gblk = cta + lb * G;
+        const int pair = gblk / nblocks, b = gblk - pair * nblocks;
+        const int by = b / a.gw, bx = b - by * a.gw;
+        const short2 pred = a.mv[(size_t)pair * a.mv_plane + b];
+        const int x2 = bx * BS + pred.x, y2 = by * BS + pred.y;
+        const int valid = !(x2 < 0 || y2 < 0 || x2 + BS > a.w || y2 + BS > a.h);
+        StageMeta m;
+        m.x2 = x2; m.y2 = y2; m.predx = pred.x; m.predy = pred.y;
+        m.valid = valid; m.band = band; m.bslot = lb % kBlockSlots; m.gblk = gblk;
+        s_meta[stage] = m;
+        if (valid) {
+          uint8_t* st = smem + (size_t)stage * a.stage_bytes;
+          mbar_arrive_expect_tx(&s_full[stage], (uint32_t)(4 * a.box_bytes + a.blk_bytes));
+          const int wx = x2 - a.R, wy = y2 - a.R + band * a.band_rows;
+#pragma unroll
+          for (int s = 0; s < 4; ++s)
+            tma_load_3d(st + (size_t)s * a.copy_words * 4, &map_win, &s_full[stage], wx + s, wy - s * a.skew, pair);
+          tma_load_3d(st + (size_t)4 * a.copy_words * 4, &map_blk, &s_full[stage], bx * BS, by * BS, pair);
+        } else {
+          mbar_arrive(&s_full[stage]);
+        }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumers
+  for (;;) {
+    uint32_t t = 0;
+    if (lane == 0) t = atomicAdd(&s_next, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    const int k = (int)(t / (uint32_t)a.wi_max);
+    const int j = (int)t - k * a.wi_max;
+    if (k >= my_units) break;
+    const int stage = k % kStages;
+    mbar_wait(&s_full[stage], (uint32_t)(k / kStages) & 1u);
+    const StageMeta m = s_meta[stage];
+
+    if (m.valid) {
+      const int segs_here = min(a.segs_per_band, a.segs_total - m.band * a.segs_per_band);
+      const int items = a.n * segs_here;
+      const int q = j * 32 + lane;
+      if (j * 32 < items) {
+        const bool active = q < items;
+        const int qq = active ? q : 0;
+        const int sidx = qq / a.n, o = qq - sidx * a.n;
+        const int sh = o & 3, wi = o >> 2;
+        const int cy0 = sidx * SEG;
+        const uint8_t* st = smem + (size_t)stage * a.stage_bytes;
+        const uint32_t* win = reinterpret_cast<const uint32_t*>(st) + (size_t)sh * a.copy_words +
+                              (size_t)(cy0 + sh * a.skew) * a.pww + wi;
+        const uint8_t* blk = st + (size_t)4 * a.copy_words * 4;
+
+        uint32_t acc[SEG];
+#pragma unroll
+        for (int c = 0; c < SEG; ++c) acc[c] = 0u;
+
+#pragma unroll 1
+        for (int qi = 0; qi < QN * QN; ++qi) {
+          const int qy = qi / QN, qx = qi - qy * QN;
+          uint32_t A[TW][TWW];
+#pragma unroll
+          for (int y = 0; y < TW; ++y) {
+            const uint8_t* ar = blk + (size_t)(qy * TW + y) * AP + qx * TW;
+            if (TWW == 4) {
+              const uint4 v = *reinterpret_cast<const uint4*>(ar);
+              A[y][0] = v.x; A[y][1] = v.y; A[y][2 % TWW] = v.z; A[y][3 % TWW] = v.w;
+            } else {
+              const uint2 v = *reinterpret_cast<const uint2*>(ar);
+              A[y][0] = v.x; A[y][1 % TWW] = v.y;
+            }
+          }
+          const uint32_t* wb = win + (size_t)(qy * TW) * a.pww + qx * TWW;
+#pragma unroll
+          for (int jr = 0; jr < SEG + TW - 1; ++jr) {
+            uint32_t wv[TWW];
+#pragma unroll
+            for (int kk = 0; kk < TWW; ++kk) wv[kk] = wb[kk];
+            wb += a.pww;
+#pragma unroll
+            for (int kk = 0; kk < TWW; ++kk) {
+#pragma unroll
+              for (int y = 0; y < TW; ++y) {
+                const int c = jr - y;
+                if (c >= 0 && c < SEG) acc[c] = sad4(A[y][kk], wv[kk], acc[c]);
+              }
+            }
+          }
+        }
+
+        // lane-local argmin on (SAD, spiral rank); rank only computed when the SAD can still win
+        unsigned long long best = ~0ull;
+        const int dx = o - a.R;
+        const int px = m.x2 + dx;
+        const bool xok = active && px >= 0 && px + BS <= a.w;
+        const int dy0 = m.band * a.band_rows + cy0 - a.R;
+#pragma unroll
+        for (int c = 0; c < SEG; ++c) {
+          const int dy = dy0 + c;
+          const int py = m.y2 + dy;
+          const bool ok = xok && dy <= a.R && py >= 0 && py + BS <= a.h;
+          if (ok && acc[c] <= (uint32_t)(best >> 32)) {
+            const unsigned long long key = ((unsigned long long)acc[c] << 32) | spiral_rank(dx, dy);
+            best = key < best ? key : best;
+          }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, off);
+          best = other < best ? other : best;
+        }
+        if (lane == 0 && best != ~0ull) atomicMin(&s_bkey[m.bslot], best);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      const uint32_t d = atomicAdd(&s_sdone[stage], 1u);
+      if (d == (uint32_t)a.wi_max - 1u) {
+        // last work item of this unit: maybe last unit of the block
+        s_sdone[stage] = 0;
+        const uint32_t bd = atomicAdd(&s_bdone[m.bslot], 1u);
+        if (bd == (uint32_t)a.nbands - 1u) {
+          __threadfence_block();
+          const unsigned long long key = *reinterpret_cast<volatile unsigned long long*>(&s_bkey[m.bslot]);
+          s_bkey[m.bslot] = ~0ull;
+          s_bdone[m.bslot] = 0;
+          const int pair = m.gblk / nblocks, b = m.gblk - pair * nblocks;
+          short2 out = make_short2(0, 0);
+          if (m.valid) {
+            int dx, dy;
+            spiral_unrank((uint32_t)key, dx, dy);
+            out = make_short2((short)(m.predx + dx), (short)(m.predy + dy));
+            if (a.counters) {
+              const int nx = min(a.R, a.w - BS - m.x2) - max(-a.R, -m.x2) + 1;
+              const int ny = min(a.R, a.h - BS - m.y2) - max(-a.R, -m.y2) + 1;
+              atomicAdd(&a.counters[0], (unsigned long long)(nx * ny));
+              atomicAdd(&a.counters[1], (unsigned long long)(nx * ny) * (unsigned long long)(BS * BS));
+            }
+          }
+          a.mv[(size_t)pair * a.mv_plane + b] = out;
+        }
+        __threadfence_block();
+        mbar_arrive(&s_empty[stage]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+static int encode_u8_3d(CUtensorMap* map, const uint8_t* base, int w, int h, int pitch, size_t plane, int n,
+                        int box_w, int box_h) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return -1;
+  cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)plane};
+  cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+static int pick_seg(int bs, int R) {
+  // lane efficiency of the flattened (column, segment) item space; candidates: instantiated SEG values
+  const int n = 2 * R + 1;
+  const int cands[3] = {13, 11, 8};
+  int best = 13;
+  double best_eff = -1.0;
+  for (int i = 0; i < 3; ++i) {
+    const int seg = cands[i];
+    const int segs = (n + seg - 1) / seg;
+    const int items = n * segs;
+    const int wi = (items + 31) / 32;
+    // useful SADs / issued SADs, discounted by the per-item row overhead (SEG + T - 1 rows of loads)
+    const int T = bs >= 16 ? 16 : bs;
+    double eff = (double)(n * n) / ((double)wi * 32.0 * seg);
+    eff *= (double)seg / (double)(seg + 0.06 * (seg + T - 1));
+    if (eff > best_eff) { best_eff = eff; best = seg; }
+  }
+  return best;
+}
+
+struct TmaGeom {
+  TmaSearchArgs a;
+  int seg;
+  int box_w, box_h;
+  size_t smem;
+};
+
+static bool make_geom(int w, int h, int bs, int R, TmaGeom* g) {
+  if (!(bs == 8 || bs == 16 || bs == 32)) return false;
+  if (R < 1) return false;
+  memset(g, 0, sizeof(*g));
+  const int n = 2 * R + 1;
+  const int seg = pick_seg(bs, R);
+  int words = ((2 * R) >> 2) + bs / 4;
+  int box_w = ((words * 4 + 15) / 16) * 16;
+  if ((box_w / 4) % 8 != 4) box_w += 16;  // row pitch == 4 (mod 8) words so that a row skew rotates banks by 8
+  if (box_w > 256) return false;
+  const int pww = box_w / 4;
+  int skew = 0;
+  for (int m = 1; m < 8; ++m)
+    if ((m * pww) % 32 == 8) { skew = m; break; }
+  if (!skew) return false;
+  const int segs_total = (n + seg - 1) / seg;
+  const int blk_bytes = bs * (bs >= 16 ? bs : 16);
+  const size_t budget = 36 * 1024;  // per stage: kStages * 2 CTAs/SM must fit 227 KB
+  int spb = segs_total;
+  for (;;) {
+    const int box_h = spb * seg + bs - 1 + 3 * skew;
+    const size_t copy_bytes = (((size_t)box_h * box_w) + 127) / 128 * 128;
+    const size_t stage = 4 * copy_bytes + ((blk_bytes + 127) / 128) * 128;
+    if ((stage <= budget && box_h <= 256) || spb == 1) {
+      if (stage > 72 * 1024 || box_h > 256) return false;
+      g->box_h = box_h;
+      g->a.copy_words = (int)(copy_bytes / 4);
+      g->a.stage_bytes = (int)stage;
+      break;
+    }
+    --spb;
+  }
+  g->seg = seg;
+  g->box_w = box_w;
+  g->a.w = w; g->a.h = h;
+  g->a.gw = w / bs; g->a.gh = h / bs;
+  g->a.R = R; g->a.n = n;
+  g->a.segs_total = segs_total;
+  g->a.segs_per_band = spb;
+  g->a.nbands = (segs_total + spb - 1) / spb;
+  g->a.band_rows = spb * seg;
+  g->a.wi_max = (n * spb + 31) / 32;
+  g->a.pww = pww;
+  g->a.skew = skew;
+  g->a.box_bytes = g->box_h * box_w;
+  g->a.blk_bytes = blk_bytes;
+  g->smem = (size_t)kStages * g->a.stage_bytes;
+  return true;
+}
+
+template <int BS, int SEG>
+static void launch_inst(const TmaSearchPlan& plan, const TmaSearchArgs& a, int grid, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(k_search_tma<BS, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    configured = true;
+  }
+  k_search_tma<BS, SEG><<<grid, kThreads, plan.smem_bytes, s>>>(plan.map_win, plan.map_blk, a);
+}
+
+int tma_search_plan(TmaSearchPlan* plan, const uint8_t* img1, const uint8_t* img2, int w, int h, int pitch,
+                    size_t plane, int n_planes, int bs, int R, char* err, size_t errlen) {
+  memset(plan, 0, sizeof(*plan));
+  TmaGeom g;
+  if (!make_geom(w, h, bs, R, &g)) return 0;  // not supported: caller uses the generic kernel
+  if (!get_encode()) {
+    if (err) snprintf(err, errlen, "cuTensorMapEncodeTiled entry point not available");
+    return -1;
+  }
+  if (encode_u8_3d(&plan->map_win, img2, w, h, pitch, plane, n_planes, g.box_w, g.box_h) != 0 ||
+      encode_u8_3d(&plan->map_blk, img1, w, h, pitch, plane, n_planes, bs >= 16 ? bs : 16, bs) != 0) {
+    if (err) snprintf(err, errlen, "cuTensorMapEncodeTiled failed (w=%d h=%d pitch=%d box=%dx%d)", w, h, pitch, g.box_w, g.box_h);
+    return -1;
+  }
+  plan->supported = 1;
+  plan->bs = bs;
+  plan->R = R;
+  plan->seg = g.seg;
+  plan->band_rows = g.a.band_rows;
+  plan->box_w = g.box_w;
+  plan->box_h = g.box_h;
+  plan->n_box_x = 1;
+  plan->threads = kThreads;
+  plan->stages = kStages;
+  plan->smem_bytes = g.smem;
+  return 0;
+}
+
+void launch_search_tma(const TmaSearchPlan& plan, ImgView i1, ImgView i2, MvView mv, int n,
+                       unsigned long long* counters, int sm_count, cudaStream_t s) {
+  (void)i2;
+  TmaGeom g;
+  make_geom(i1.w, i1.h, plan.bs, plan.R, &g);
+  TmaSearchArgs a = g.a;
+  a.n_pairs = n;
+  a.mv = mv.p;
+  a.mv_plane = mv.plane;
+  a.counters = counters;
+  const int total = a.gw * a.gh * n;
+  int grid = sm_count * 2;
+  if (grid > total) grid = total;
+#define BBME_CASE(BS_, SEG_) \
+  if (plan.bs == BS_ && plan.seg == SEG_) { launch_inst<BS_, SEG_>(plan, a, grid, s); return; }
+  BBME_CASE(8, 13) BBME_CASE(8, 11) BBME_CASE(8, 8)
+  BBME_CASE(16, 13) BBME_CASE(16, 11) BBME_CASE(16, 8)
+  BBME_CASE(32, 13) BBME_CASE(32, 11) BBME_CASE(32, 8)
+#undef BBME_CASE
+}
+
+}  // namespace bbme

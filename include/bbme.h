@@ -1,0 +1,169 @@
+/*
+ * bbme.h -- C ABI of the B200 block-matching motion estimator (libbbme.so).
+ *
+ * This is the drop-in boundary for ONE path of ashish-nr/BlockBasedMotionEstimation:
+ *     MF::MF + MF::calcMotionBlockMatching          (reference motion_framework.h:12-13, motion_framework.cpp:4-219)
+ *     Flow::ReadFlowFile / WriteFlowFile / CalculateMSE (reference rw_flow.h:17-22, rw_flow.cpp:50-200,309-332)
+ * The reference has no FFI of its own (it is one C++ program); include/motion_framework.h and
+ * include/rw_flow.h re-create its C++ classes on top of the functions below, and INTEGRATION.md shows the
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 (BBME_OK) or a negative bbme_status;
+ * bbme_last_error() gives the text.  A context owns one CUDA device, its streams and all device memory.
+ * One context per GPU per host thread; calls on one context are not re-entrant (same as one MF object,
+ * motion_framework.h:38-39).  There is no CPU fallback: without a usable CUDA device bbme_create fails.
+ *
+ * Index 0 of search_size[] / block_size[] is the finest pyramid level (motion_framework.cpp:67-74).
+ * "search range +-R" in the reference's vocabulary is search_size = block_size + 2R (motion_framework.cpp:299).
+ */
+#ifndef BBME_H
+#define BBME_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BBME_MAX_LEVELS 16
+#define BBME_VERSION 100
+
+typedef enum {
+  BBME_OK = 0,
+  BBME_E_ARG = -1,        /* null pointer, non-positive size, block size not a power of two in [2,128], ... */
+  BBME_E_NOPAD = -2,      /* reference prints "Could not find any multiples of the block size..." and exits, motion_framework.cpp:21-26 */
+  BBME_E_ODD_PAD = -3,    /* (padded - original) is odd: the reference pads floor(diff/2) per side and then reads out of bounds */
+  BBME_E_ONE_BLOCK = -4,  /* fewer than 2 blocks on an axis at some level: the reference reads out of bounds, motion_framework.cpp:475 */
+  BBME_E_NOMEM = -5,
+  BBME_E_CUDA = -6,       /* CUDA runtime/driver failure, including "no device" */
+  BBME_E_STATE = -7,      /* call order: estimate before plan, batch larger than planned, ... */
+  BBME_E_IO = -8,         /* .flo: cannot open / short write */
+  BBME_E_FORMAT = -9,     /* .flo: wrong extension, tag, size, truncated or trailing bytes */
+  BBME_E_RANGE = -10      /* motion vectors would not fit int16 (image side > 16383) */
+} bbme_status;
+
+typedef struct bbme_ctx bbme_ctx;
+
+/* What MF publishes after construction (motion_framework.h:16-19) plus the pyramid geometry. */
+typedef struct {
+  int width, height;                 /* original */
+  int padded_width, padded_height;   /* MF::padded_width / padded_height */
+  int padding_x, padding_y;          /* MF::padding_x / padding_y */
+  int num_levels;
+  int level_width[BBME_MAX_LEVELS];
+  int level_height[BBME_MAX_LEVELS];
+  int block_size[BBME_MAX_LEVELS];
+  int search_size[BBME_MAX_LEVELS];
+} bbme_shape;
+
+/* Device-side timing and work counters of the last estimate call (all pairs of the call together). */
+typedef struct {
+  float ms_total;          /* CUDA-event time of the whole device pipeline, copies excluded */
+  float ms_pyramid;        /* pad + pyrDown */
+  float ms_search;         /* all levels */
+  float ms_regularize;     /* all sweeps, splits and fix-up rounds */
+  float ms_other;          /* MV upsample + export */
+  uint32_t kernel_launches;
+  uint32_t fix_rounds;     /* total fixed-point rounds after the first full sweep pass */
+  uint32_t fix_blocks;     /* blocks re-evaluated in those rounds */
+  uint32_t reserved;
+  uint64_t search_candidates; /* in-bounds candidate positions evaluated (== oracle search_sad_calls) */
+  uint64_t search_absdiffs;   /* pixels |a-b| in the search (== oracle search_absdiffs) */
+} bbme_stats;
+
+typedef struct {
+  int sweeps;          /* regularisation sweeps per block size; reference hard-codes 2 (motion_framework.cpp:143,184) */
+  int chunk_pairs;     /* pairs resident on the device per pipeline slot (>=1) */
+  int slots;           /* pipeline slots (1..4); >1 overlaps H2D / compute / D2H of successive chunks */
+  int search_kernel;   /* 0 = auto, 1 = force the generic kernel, 2 = force the TMA kernel (error if unsupported) */
+  int collect_stats;   /* 1 = per-stage CUDA-event timing + work counters (adds synchronisation) */
+  int keep_search_mv;  /* 1 = keep a copy of every level's field after the search (for bbme_debug_level_mv) */
+} bbme_options;
+
+void bbme_default_options(bbme_options* o);
+
+int bbme_version(void);
+const char* bbme_status_string(int status);
+
+/* Shape only, no device needed: the padding search of MF::MF (motion_framework.cpp:15-54). */
+int bbme_plan_shape(int width, int height, int num_levels, const int* search_size, const int* block_size,
+                    bbme_shape* out);
+
+int bbme_create(bbme_ctx** ctx, int device);
+void bbme_destroy(bbme_ctx* ctx);
+const char* bbme_last_error(const bbme_ctx* ctx); /* ctx may be NULL: error of the last failed bbme_create */
+
+/* Fixes geometry and parameters, allocates device memory, encodes TMA descriptors.  Replaces the parameter
+ * half of MF::MF(image1, image2, search_size, block_size, num_levels) (motion_framework.h:12). */
+int bbme_plan(bbme_ctx* ctx, int width, int height, int num_levels, const int* search_size,
+              const int* block_size, const bbme_options* opt, bbme_shape* out);
+
+/* One pair, host buffers: MF::MF (pad + pyramid) followed by MF::calcMotionBlockMatching.
+ * im1/im2: 8-bit luma, `pitch_bytes` between rows.  flow: padded_height x padded_width x 2 float32 (u,v),
+ * the CV_32FC2 field the reference returns (motion_framework.cpp:218). */
+int bbme_estimate(bbme_ctx* ctx, const uint8_t* im1, const uint8_t* im2, size_t pitch_bytes, float* flow);
+
+/* n independent pairs, host buffers (pinned buffers from bbme_host_alloc make the copies asynchronous).
+ * Pairs are processed in chunks of chunk_pairs over `slots` streams. */
+int bbme_estimate_batch(bbme_ctx* ctx, int n, const uint8_t* const* im1, const uint8_t* const* im2,
+                        size_t pitch_bytes, float* const* flow);
+
+/* n <= chunk_pairs pairs already in device memory (same device as the context).  Frames are n planes of
+ * `plane_stride` bytes; flow is n planes of flow_plane_stride floats.  Runs on slot 0's stream and returns
+ * after enqueueing; call bbme_sync before reading.  This is the "inputs resident in HBM" entry point. */
+int bbme_estimate_device(bbme_ctx* ctx, int n, const uint8_t* d_im1, const uint8_t* d_im2, size_t pitch_bytes,
+                         size_t plane_stride, float* d_flow, size_t flow_plane_stride);
+
+/* Compact result of the same computation: the 2x2-granular int16 field (padded_height/2 x padded_width/2 x 2),
+ * i.e. the information content of the dense float field (motion_framework.cpp:205-206 replicates it 2x2). */
+int bbme_estimate_device_compact(bbme_ctx* ctx, int n, const uint8_t* d_im1, const uint8_t* d_im2,
+                                 size_t pitch_bytes, size_t plane_stride, int16_t* d_mv, size_t mv_plane_stride);
+
+int bbme_sync(bbme_ctx* ctx);
+int bbme_get_stats(bbme_ctx* ctx, bbme_stats* out);
+int bbme_get_shape(const bbme_ctx* ctx, bbme_shape* out);
+
+/* Pinned host memory for asynchronous copies. */
+int bbme_host_alloc(void** p, size_t bytes);
+void bbme_host_free(void* p);
+
+/* ---- state of the last bbme_estimate* call on slot 0, for per-stage parity tests (host output buffers) ---- */
+/* frame: 0 = image1, 1 = image2.  out: level_height x level_width bytes, dense. */
+int bbme_debug_level_image(bbme_ctx* ctx, int pair, int frame, int level, uint8_t* out);
+/* which: 0 = after the whole regularisation schedule (2x2-granular: level_height/2 x level_width/2 x 2 int16),
+ *        1 = after the search (block-granular: level_height/bs x level_width/bs x 2 int16; needs keep_search_mv). */
+int bbme_debug_level_mv(bbme_ctx* ctx, int pair, int level, int which, int16_t* out);
+
+/* ---- single stages on host buffers (upload, one kernel, download): parity tests against the oracle ---- */
+/* cv::pyrDown(src, Size(w/2, h/2)), motion_framework.cpp:89-90. */
+int bbme_stage_pyrdown(bbme_ctx* ctx, const uint8_t* src, int w, int h, uint8_t* dst);
+/* MF::calcLevelBM (motion_framework.cpp:226-244) on one level.  mv: (h/bs) x (w/bs) x 2 int16, holds the
+ * prediction on entry and the result on exit.  kernel: as bbme_options.search_kernel. */
+int bbme_stage_search(bbme_ctx* ctx, const uint8_t* im1, const uint8_t* im2, int w, int h, int block_size,
+                      int search_size, int16_t* mv, int kernel, bbme_stats* st);
+/* One MF::regularize_MVs sweep (motion_framework.cpp:424-530) with in-place raster semantics.
+ * lambda is the level's current lambda, lambda_multiplier the sweep's multiplier (motion_framework.cpp:607). */
+int bbme_stage_regularize(bbme_ctx* ctx, const uint8_t* im1, const uint8_t* im2, int w, int h, int block_size,
+                          float lambda, int lambda_multiplier, int16_t* mv, uint32_t* rounds_out);
+/* MF::divide_blocks (motion_framework.cpp:845-862): (h/bs) x (w/bs) field -> (2h/bs) x (2w/bs). */
+int bbme_stage_divide(bbme_ctx* ctx, const int16_t* mv_in, int gw, int gh, int16_t* mv_out);
+/* MF::copyMVs (motion_framework.cpp:828-843): coarse 2x2-granular final field (ch/2 x cw/2) ->
+ * fine prediction at fine_block_size granularity ((2ch/fbs) x (2cw/fbs)). */
+int bbme_stage_copy_mvs(bbme_ctx* ctx, const int16_t* coarse_mv, int cw, int ch, int coarse_block_size,
+                        int fine_block_size, int16_t* fine_pred);
+
+/* ---- .flo codec and the endpoint-error metric (host code; rw_flow.cpp) ---- */
+int bbme_flo_read_header(const char* path, int* width, int* height);
+int bbme_flo_read(const char* path, float* data, int width, int height);          /* Flow::ReadFlowFile */
+int bbme_flo_write(const char* path, const float* data, int width, int height);   /* Flow::WriteFlowFile */
+/* Flow::CalculateMSE: average endpoint error over gt-known pixels (rw_flow.cpp:309-332). */
+double bbme_flow_aee(const float* gt, const float* flow, int width, int height);
+/* main()'s post-processing (main_class.cpp:58-70): strip padding, keep every `factor`-th pixel, divide by factor.
+ * out: (height/factor) x (width/factor) x 2 with width/height the ORIGINAL (pre-padding) size. */
+int bbme_flow_strip_subsample(const float* padded_flow, const bbme_shape* shape, int factor, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BBME_H */

@@ -1,0 +1,2 @@
+// cvshim: see opencv2/core/core.hpp
+#include "../core/core.hpp"
