@@ -29,7 +29,7 @@ class BbmeStats(C.Structure):
         ("ms_total", C.c_float), ("ms_pyramid", C.c_float), ("ms_search", C.c_float),
         ("ms_regularize", C.c_float), ("ms_other", C.c_float),
         ("kernel_launches", C.c_uint32), ("fix_rounds", C.c_uint32), ("fix_blocks", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("search_kernel_used", C.c_uint32), ("search_launches", C.c_uint32), ("reserved", C.c_uint32),
         ("search_candidates", C.c_uint64), ("search_absdiffs", C.c_uint64),
     ]
 
@@ -60,6 +60,8 @@ SIGNATURES = {
     "bbme_estimate_device_compact": (_I, [_P, _I, _P, _P, _SZ, _SZ, _P, _SZ]),
     "bbme_sync": (_I, [_P]),
     "bbme_get_stats": (_I, [_P, C.POINTER(BbmeStats)]),
+    "bbme_set_streams": (_I, [_P, _I, C.POINTER(_P)]),
+    "bbme_measure_int_peak": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "bbme_get_shape": (_I, [_P, C.POINTER(BbmeShape)]),
     "bbme_host_alloc": (_I, [C.POINTER(_P), _SZ]),
     "bbme_host_free": (None, [_P]),

@@ -174,6 +174,17 @@ class Estimator:
                                                       int(plane), C.c_void_p(d_mv), int(mv_plane)),
                "bbme_estimate_device_compact")
 
+    def set_streams(self, handles):
+        """Run slot i on the caller's CUDA stream handles[i] (e.g. torch.cuda.Stream().cuda_stream)."""
+        arr = (C.c_void_p * len(handles))(*[C.c_void_p(int(h)) for h in handles])
+        _check(self._lib, self._ctx, self._lib.bbme_set_streams(self._ctx, len(handles), arr), "bbme_set_streams")
+
+    def measure_int_peak(self):
+        """(|a-b| per second, SM MHz) of a live VABSDIFF4 issue-rate micro-benchmark on this device."""
+        v, f = C.c_double(0), C.c_double(0)
+        _check(self._lib, self._ctx, self._lib.bbme_measure_int_peak(self._ctx, C.byref(v), C.byref(f)), "bbme_measure_int_peak")
+        return v.value, f.value
+
     def sync(self):
         _check(self._lib, self._ctx, self._lib.bbme_sync(self._ctx), "bbme_sync")
 

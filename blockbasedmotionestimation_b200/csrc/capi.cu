@@ -20,6 +20,7 @@ thread_local std::string g_create_error;
 
 struct Slot {
   cudaStream_t stream = nullptr;
+  bool own_stream = true;
   uint8_t* in1 = nullptr;  // staged host frames: chunk planes of in_pitch x height
   uint8_t* in2 = nullptr;
   uint8_t* img[2][kMaxLevels] = {};
@@ -40,7 +41,7 @@ struct Slot {
   int last_n = 0;
 };
 
-enum { TAG_PYR = 0, TAG_SEARCH = 1, TAG_REG = 2, TAG_OTHER = 3 };
+enum { TAG_PYR = 0, TAG_SEARCH = 1, TAG_REG = 2, TAG_OTHER = 3, TAG_BEGIN = 4 };
 
 }  // namespace
 
@@ -61,6 +62,8 @@ struct bbme_ctx {
   std::vector<void*> allocs;
   bbme_stats stats{};
   uint32_t launches = 0;
+  uint32_t search_launches = 0;
+  bool stats_armed = false;
 };
 
 namespace {
@@ -104,7 +107,7 @@ int dev_alloc(bbme_ctx* c, T** p, size_t count, bool zero) {
 void release_plan(bbme_ctx* c) {
   for (Slot& s : c->slots) {
     for (cudaEvent_t e : s.ev) cudaEventDestroy(e);
-    if (s.stream) cudaStreamDestroy(s.stream);
+    if (s.stream && s.own_stream) cudaStreamDestroy(s.stream);
   }
   c->slots.clear();
   for (void* p : c->allocs) cudaFree(p);
@@ -173,6 +176,7 @@ void fold_events(bbme_ctx* c, Slot& s) {
   if (s.ev.size() >= 2) {
     for (size_t i = 1; i < s.ev.size(); ++i) {
       float ms = 0.f;
+      if (s.ev_tag[i] == TAG_BEGIN) continue;  // gap between two chunks on this stream (copies, idle)
       if (cudaEventElapsedTime(&ms, s.ev[i - 1], s.ev[i]) != cudaSuccess) continue;
       switch (s.ev_tag[i]) {
         case TAG_PYR: c->stats.ms_pyramid += ms; break;
@@ -194,12 +198,8 @@ int run_chunk(bbme_ctx* c, Slot& s, int n, const uint8_t* d_in1, const uint8_t* 
   const bbme_shape& sh = c->shape;
   const int L = sh.num_levels;
   cudaStream_t st = s.stream;
-  s.last_n = n;
-  if (c->opt.collect_stats) {
-    cudaMemsetAsync(s.counters, 0, 2 * sizeof(unsigned long long), st);
-    cudaMemset2DAsync(s.ctr + CTR_ROUNDS, kCtrWords * sizeof(uint32_t), 0, 2 * sizeof(uint32_t), n, st);
-  }
-  mark(c, s, TAG_OTHER);
+  s.last_n = n > s.last_n ? n : s.last_n;
+  mark(c, s, TAG_BEGIN);
   // ---- MF::MF: pad + Gaussian pyramid (motion_framework.cpp:57-106)
   launch_pad(d_in1, d_in2, in_pitch, in_plane, sh.width, sh.height, sh.padding_x, sh.padding_y, s.img[0][0],
              s.img[1][0], c->pitch[0], c->plane[0], sh.padded_width, sh.padded_height, n, st);
@@ -234,6 +234,7 @@ int run_chunk(bbme_ctx* c, Slot& s, int n, const uint8_t* d_in1, const uint8_t* 
     if (use_tma) launch_search_tma(s.tma[l], i1, i2, field, n, ctrs, c->sm_count, st);
     else launch_search_generic(i1, i2, field, g, R, n, ctrs, st);
     ++c->launches;
+    ++c->search_launches;
     mark(c, s, TAG_SEARCH);
     if (c->opt.keep_search_mv && s.mv_search[l]) {
       cudaMemcpy2DAsync(s.mv_search[l], (size_t)gw * gh * sizeof(short2), cur, c->cap[l] * sizeof(short2),
@@ -294,7 +295,7 @@ int run_chunk(bbme_ctx* c, Slot& s, int n, const uint8_t* d_in1, const uint8_t* 
 }
 
 int collect_after_sync(bbme_ctx* c) {
-  if (!c->opt.collect_stats) return BBME_OK;
+  if (!c->opt.collect_stats || !c->stats_armed) return BBME_OK;
   for (Slot& s : c->slots) {
     fold_events(c, s);
     if (s.last_n > 0) {
@@ -311,6 +312,8 @@ int collect_after_sync(bbme_ctx* c) {
       s.last_n = 0;
     }
   }
+  c->stats.search_launches = c->search_launches;
+  c->stats_armed = false;
   return BBME_OK;
 }
 
@@ -319,9 +322,21 @@ int sync_all(bbme_ctx* c) {
   return BBME_OK;
 }
 
+// Start of an estimate call: reset the stats and (asynchronously, on each slot's stream) the device counters.
 void begin_call(bbme_ctx* c) {
   memset(&c->stats, 0, sizeof(c->stats));
   c->launches = 0;
+  c->search_launches = 0;
+  if (!c->opt.collect_stats) return;
+  for (Slot& s : c->slots) {
+    for (cudaEvent_t e : s.ev) cudaEventDestroy(e);
+    s.ev.clear();
+    s.ev_tag.clear();
+    s.last_n = 0;
+    cudaMemsetAsync(s.counters, 0, 2 * sizeof(unsigned long long), s.stream);
+    cudaMemset2DAsync(s.ctr + CTR_ROUNDS, kCtrWords * sizeof(uint32_t), 0, 2 * sizeof(uint32_t), c->opt.chunk_pairs, s.stream);
+  }
+  c->stats_armed = true;
 }
 
 }  // namespace
@@ -472,6 +487,36 @@ int bbme_sync(bbme_ctx* c) {
   return collect_after_sync(c);
 }
 
+int bbme_set_streams(bbme_ctx* c, int n, void* const* streams) {
+  if (!c || !streams) return BBME_E_ARG;
+  if (!c->planned) return fail(c, BBME_E_STATE, "bbme_set_streams before bbme_plan");
+  if (n != (int)c->slots.size()) return fail(c, BBME_E_ARG, "bbme_set_streams: %d streams for %zu slots", n, c->slots.size());
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  int rc = sync_all(c);
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i) {
+    Slot& s = c->slots[i];
+    if (s.stream && s.own_stream) cudaStreamDestroy(s.stream);
+    s.stream = reinterpret_cast<cudaStream_t>(streams[i]);
+    s.own_stream = false;
+  }
+  return BBME_OK;
+}
+
+int bbme_measure_int_peak(bbme_ctx* c, double* absdiff_per_s, double* sm_mhz) {
+  if (!c || !absdiff_per_s) return BBME_E_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  double best = 0.0, mhz = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    double v = 0.0, f = 0.0;
+    if (measure_int_peak(c->sm_count, &v, &f) != 0) return fail(c, BBME_E_CUDA, "int-peak micro-benchmark failed");
+    if (v > best) { best = v; mhz = f; }
+  }
+  *absdiff_per_s = best;
+  if (sm_mhz) *sm_mhz = mhz;
+  return BBME_OK;
+}
+
 int bbme_get_stats(bbme_ctx* c, bbme_stats* out) {
   if (!c || !out) return BBME_E_ARG;
   *out = c->stats;
@@ -494,11 +539,6 @@ int bbme_estimate_batch(bbme_ctx* c, int n, const uint8_t* const* im1, const uin
   for (int start = 0; start < n; start += chunk, ++ci) {
     Slot& s = c->slots[ci % c->slots.size()];
     const int m = (n - start < chunk) ? (n - start) : chunk;
-    if (c->opt.collect_stats && ci >= (int)c->slots.size()) {  // slot reuse: fold its previous chunk first
-      CUDA_TRY(c, cudaStreamSynchronize(s.stream));
-      int rc0 = collect_after_sync(c);
-      if (rc0) return rc0;
-    }
     for (int i = 0; i < m; ++i) {
       CUDA_TRY(c, cudaMemcpy2DAsync(s.in1 + (size_t)i * c->in_plane, c->in_pitch, im1[start + i], pitch, c->shape.width,
                                     c->shape.height, cudaMemcpyHostToDevice, s.stream));
@@ -534,11 +574,6 @@ static int estimate_device_impl(bbme_ctx* c, int n, const uint8_t* d1, const uin
   for (int start = 0; start < n; start += chunk, ++ci) {
     Slot& s = c->slots[ci % c->slots.size()];
     const int m = (n - start < chunk) ? (n - start) : chunk;
-    if (c->opt.collect_stats && ci >= (int)c->slots.size()) {
-      CUDA_TRY(c, cudaStreamSynchronize(s.stream));
-      int rc0 = collect_after_sync(c);
-      if (rc0) return rc0;
-    }
     int rc = run_chunk(c, s, m, d1 + (size_t)start * plane, d2 + (size_t)start * plane, pitch, plane,
                        d_flow ? d_flow + (size_t)start * flow_plane : nullptr, flow_plane,
                        d_mv ? d_mv + (size_t)start * mv_plane : nullptr, mv_plane);
@@ -701,7 +736,8 @@ int bbme_stage_search(bbme_ctx* c, const uint8_t* im1, const uint8_t* im2, int w
     st->kernel_launches = 1;
     st->search_candidates = hc[0];
     st->search_absdiffs = hc[1];
-    st->reserved = plan.supported ? 2u : 1u;
+    st->search_kernel_used = plan.supported ? 2u : 1u;
+    st->search_launches = 1;
   }
   return BBME_OK;
 }

@@ -55,55 +55,78 @@ void launch_pad(const uint8_t* in1, const uint8_t* in2, size_t in_pitch, size_t 
 
 // ============================================================================================ pyrDown
 // cv::pyrDown(src, dst, Size(cols/2, rows/2)) for 8-bit (motion_framework.cpp:89-90): 5x5 separable
-// [1 4 6 4 1], BORDER_REFLECT_101, (sum + 128) >> 8.  One thread produces 4 adjacent output pixels from
-// 5 source rows x 16 source bytes (four aligned 32-bit loads per row); HBM/L2-bound.
+// [1 4 6 4 1], BORDER_REFLECT_101, (sum + 128) >> 8.
+// One thread owns one aligned 16-byte source strip [16t, 16t+16) -> 8 output pixels; per source row it issues one
+// coalesced 128-bit load and fetches the 2-byte left / 1-byte right halo from the neighbouring lanes with two
+// shuffles (lanes at a warp or image edge read the halo bytes directly, with BORDER_REFLECT_101).  HBM/L2-bound.
 __device__ __forceinline__ int reflect101(int p, int len) {
   if (p < 0) p = -p;
   if (p >= len) p = 2 * len - 2 - p;
   return p;
 }
 
-__global__ void __launch_bounds__(256) k_pyrdown(ImgView s1, ImgView s2, uint8_t* __restrict__ d1,
+__global__ void __launch_bounds__(128) k_pyrdown(ImgView s1, ImgView s2, uint8_t* __restrict__ d1,
                                                  uint8_t* __restrict__ d2, int dw, int dh, int dpitch, size_t dplane) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;  // 4 output pixels: x = 4t .. 4t+3
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;  // strip index: source bytes 16t..16t+15, outputs 8t..8t+7
+  const int lane = threadIdx.x & 31;
   const int y = blockIdx.y;
   const int pair = blockIdx.z >> 1;
   const int frame = blockIdx.z & 1;
-  if (4 * t >= dw || y >= dh) return;
   const ImgView sv = frame ? s2 : s1;
   const uint8_t* src = sv.p + (size_t)pair * sv.plane;
-  uint8_t* dst = (frame ? d2 : d1) + (size_t)pair * dplane + (size_t)y * dpitch + 4 * t;
   const int sw = sv.w, sh = sv.h;
-  int acc[4] = {0, 0, 0, 0};
-  const int xs = 8 * t - 4;  // first source byte of the 16-byte strip
-  const bool interior = (xs >= 0) && (8 * t + 8 < sw) && (xs + 16 <= sv.pitch);
+  const bool live = 8 * t < dw;            // whole warps stay alive for the shuffles
+  const bool full = 16 * t + 16 <= sv.pitch;
+  int acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0;
 #pragma unroll
   for (int j = 0; j < 5; ++j) {
     const int wj = (j == 0 || j == 4) ? 1 : ((j == 2) ? 6 : 4);
     const uint8_t* row = src + (size_t)reflect101(2 * y + j - 2, sh) * sv.pitch;
-    int p[11];  // source pixels 8t-2 .. 8t+8
-    if (interior) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + xs)) ;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (live && full) v = __ldg(reinterpret_cast<const uint4*>(row + 16 * t));
+    // halo: bytes 16t-2, 16t-1 (high half of the left neighbour's last word) and 16t+16 (right neighbour's first byte)
+    uint32_t left = __shfl_up_sync(0xffffffffu, v.w, 1);
+    uint32_t right = __shfl_down_sync(0xffffffffu, v.x, 1);
+    int p[19];  // source pixels 16t-2 .. 16t+16
+    if (live) {
+      if (lane == 0 || t == 0) {
+        p[0] = (int)__ldg(row + reflect101(16 * t - 2, sw));
+        p[1] = (int)__ldg(row + reflect101(16 * t - 1, sw));
+      } else {
+        p[0] = (int)((left >> 16) & 0xffu);
+        p[1] = (int)(left >> 24);
+      }
+      if (lane == 31 || 16 * t + 16 >= sw) p[18] = (int)__ldg(row + reflect101(16 * t + 16, sw));
+      else p[18] = (int)(right & 0xffu);
       const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int q = 0; q < 11; ++q) p[q] = (int)((wd[(q + 2) >> 2] >> (((q + 2) & 3) * 8)) & 0xffu);
-    } else {
+      for (int q = 0; q < 16; ++q) p[2 + q] = (int)((wd[q >> 2] >> ((q & 3) * 8)) & 0xffu);
+      if (16 * t + 16 > sw || !full) {  // ragged right edge: pixels past the image width are reflected, not read from the pitch tail
 #pragma unroll
-      for (int q = 0; q < 11; ++q) p[q] = (int)__ldg(row + reflect101(8 * t - 2 + q, sw));
-    }
+        for (int q = 0; q < 16; ++q)
+          if (16 * t + q >= sw || !full) p[2 + q] = (int)__ldg(row + reflect101(16 * t + q, sw));
+      }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int hsum = p[2 * i] + 4 * p[2 * i + 1] + 6 * p[2 * i + 2] + 4 * p[2 * i + 3] + p[2 * i + 4];
-      acc[i] += wj * hsum;
+      for (int i = 0; i < 8; ++i) {
+        const int hsum = p[2 * i] + 4 * p[2 * i + 1] + 6 * p[2 * i + 2] + 4 * p[2 * i + 3] + p[2 * i + 4];
+        acc[i] += wj * hsum;
+      }
     }
   }
-  uint32_t out = 0;
+  if (!live || y >= dh) return;
+  uint8_t* dst = (frame ? d2 : d1) + (size_t)pair * dplane + (size_t)y * dpitch + 8 * t;
+  uint32_t lo = 0, hi = 0;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) out |= (uint32_t)((acc[i] + 128) >> 8) << (8 * i);
-  if (4 * t + 4 <= dw) {
-    *reinterpret_cast<uint32_t*>(dst) = out;
+  for (int i = 0; i < 4; ++i) {
+    lo |= (uint32_t)((acc[i] + 128) >> 8) << (8 * i);
+    hi |= (uint32_t)((acc[4 + i] + 128) >> 8) << (8 * i);
+  }
+  if (8 * t + 8 <= dw) {
+    *reinterpret_cast<uint2*>(dst) = make_uint2(lo, hi);
   } else {
-    for (int i = 0; 4 * t + i < dw; ++i) dst[i] = (uint8_t)(out >> (8 * i));
+    for (int i = 0; 8 * t + i < dw; ++i) dst[i] = (uint8_t)((i < 4 ? lo >> (8 * i) : hi >> (8 * (i - 4))) & 0xffu);
   }
 }
 
@@ -111,7 +134,7 @@ void launch_pyrdown(ImgView src1, ImgView src2, uint8_t* dst1, uint8_t* dst2, in
                     cudaStream_t s) {
   const int dw = src1.w / 2, dh = src1.h / 2;
   dim3 block(128);
-  dim3 grid(((dw + 3) / 4 + block.x - 1) / block.x, dh, 2 * n);
+  dim3 grid(((dw + 7) / 8 + block.x - 1) / block.x, dh, 2 * n);
   k_pyrdown<<<grid, block, 0, s>>>(src1, src2, dst1, dst2, dw, dh, dpitch, dplane);
 }
 
@@ -433,5 +456,60 @@ void launch_reg_full(const RegArgs& a, int n, cudaStream_t s) {
 }
 
 void launch_reg_fix(const RegArgs& a, int n, cudaStream_t s) { k_reg_fix<<<n, 1024, 0, s>>>(a); }
+
+
+// ============================================================================================ integer peak
+// Register-only, dependence-free VABSDIFF4.U8.ACC chains on every SM (same measurement as bench_micro/int_peak.cu).
+__global__ void __launch_bounds__(1024) k_int_peak(uint32_t* out, uint32_t seed, long long* cyc) {
+  constexpr int CH = 16, ITERS = 2048;
+  uint32_t a[CH], b[CH], acc[CH];
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    a[i] = (threadIdx.x + 1) * 0x01010101u * (i + 1) + seed;
+    b[i] = a[i] ^ 0x5a5a5a5au;
+    acc[i] = i;
+  }
+  const long long t0 = clock64();
+#pragma unroll 1
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < CH; ++i) asm volatile("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(acc[i]) : "r"(a[i]), "r"(b[i]));
+  }
+  const long long t1 = clock64();
+  uint32_t r = 0;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) r ^= acc[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+int measure_int_peak(int sm_count, double* absdiff_per_s, double* sm_mhz) {
+  uint32_t* d_out = nullptr;
+  long long* d_cyc = nullptr;
+  if (cudaMalloc(&d_out, sizeof(uint32_t) * sm_count * 1024) != cudaSuccess) return -1;
+  if (cudaMalloc(&d_cyc, sizeof(long long) * sm_count) != cudaSuccess) { cudaFree(d_out); return -1; }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  k_int_peak<<<sm_count, 1024>>>(d_out, 1u, d_cyc);
+  cudaEventRecord(e0);
+  k_int_peak<<<sm_count, 1024>>>(d_out, 2u, d_cyc);
+  cudaEventRecord(e1);
+  int rc = cudaDeviceSynchronize() == cudaSuccess ? 0 : -1;
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  long long cyc = 0;
+  cudaMemcpy(&cyc, d_cyc, sizeof(cyc), cudaMemcpyDeviceToHost);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  cudaFree(d_cyc);
+  if (rc == 0 && ms > 0.f) {
+    const double lane_ops = (double)sm_count * 1024.0 * 2048.0 * 16.0;
+    *absdiff_per_s = lane_ops * 4.0 / (ms * 1e-3);
+    *sm_mhz = (double)cyc / (ms * 1e3);
+  }
+  return rc;
+}
 
 }  // namespace bbme

@@ -53,6 +53,9 @@ void launch_export_compact(const short2* mv2, int gw2, int gh2, size_t mv_plane,
 void launch_reg_full(const RegArgs& a, int n, cudaStream_t s);
 void launch_reg_fix(const RegArgs& a, int n, cudaStream_t s);
 
+// VABSDIFF4 issue-rate micro-benchmark (kernels.cu); returns 0 on success
+int measure_int_peak(int sm_count, double* absdiff_per_s, double* sm_mhz);
+
 // ---- TMA search kernel (search_tma.cu)
 struct TmaSearchPlan {
   int supported;      // 0 if this (bs, R, geometry) is not handled by the TMA kernel

@@ -6,15 +6,17 @@
 //
 // How (B200-first, see DESIGN.md "search kernel"):
 //  * VABSDIFF4.U8.ACC issues at 64 lanes/clk/SM and shares its pipe with SHF/PRMT/LOP3 (bench_micro/int_peak.cu),
-//    so the inner loop must contain nothing but SADs.  The unaligned-window problem (displacement dx shifts the
-//    window by single bytes) is therefore solved by the copy engine, not the ALU: TMA loads FOUR copies of the
-//    search window, shifted by 0..3 bytes, so that every lane reads aligned 32-bit words.
+//    so the inner loop is kept to SADs plus the unavoidable byte alignment: displacement dx shifts the window by
+//    single bytes, and TMA tile loads need a 16-byte-aligned innermost coordinate (an unaligned one raises an
+//    illegal-instruction fault -- scripts/tma_probe.cu), so the window is staged ONCE from the aligned origin
+//    below the wanted one and each lane funnel-shifts the TWW+1 aligned words of a row into TWW words: 4 SHF feed
+//    64 SADs (6 % of the pipe).
 //  * One warp is the TMA producer (a ring of kStages stages, mbarrier full/empty); eight consumer warps pull
 //    32-lane work items from a shared counter (balances the four SM sub-partitions without CTA barriers).
 //  * A lane owns one displacement column dx and SEG consecutive dy: the 16x16 (or 8x8) block tile lives in 64
 //    (16) registers, SEG accumulators in registers, every window word loaded once per lane feeds up to 16 SADs.
-//  * Copy s is additionally staged `skew*s` rows higher, which rotates its bank mapping by 8 words: the 32 lanes
-//    of a work item (consecutive dx) read 32 distinct banks.
+//  * The 32 lanes of a work item take consecutive dx, i.e. consecutive bytes: 8-9 distinct consecutive words per
+//    shared load, conflict-free.
 //  * Block results are reduced with a 64-bit (SAD, spiral rank) key: warp shuffle -> shared atomicMin.
 #include "kernels.h"
 
@@ -39,9 +41,8 @@ struct TmaSearchArgs {
   int band_rows;       // segs_per_band * SEG
   int wi_max;          // 32-lane work items per unit (band)
   int pww;             // window row pitch in words
-  int copy_words;      // words between shifted copies
-  int skew;            // extra rows per copy index
-  int box_bytes;       // bytes of one window box
+  int win_bytes;       // bytes reserved for the window inside a stage (multiple of 128)
+  int box_bytes;       // bytes of the window box
   int blk_bytes;       // bytes of the block box
   int stage_bytes;
   short2* mv;
@@ -51,6 +52,7 @@ struct TmaSearchArgs {
 
 struct StageMeta {
   int x2, y2;      // predicted position of the block in image 2
+  int off;         // byte offset of the window's first column inside the staged (16-byte aligned) box
   int predx, predy;
   int valid;       // 0: prediction leaves the image -> MV 0, nothing staged (motion_framework.cpp:304-310)
   int band;
@@ -157,18 +159,18 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
         const short2 pred = a.mv[(size_t)pair * a.mv_plane + b];
         const int x2 = bx * BS + pred.x, y2 = by * BS + pred.y;
         const int valid = !(x2 < 0 || y2 < 0 || x2 + BS > a.w || y2 + BS > a.h);
+        const int wx = x2 - a.R;
+        const int wx_al = wx & ~15;  // floor to a multiple of 16 (two's complement, also for negative wx)
         StageMeta m;
-        m.x2 = x2; m.y2 = y2; m.predx = pred.x; m.predy = pred.y;
+        m.x2 = x2; m.y2 = y2; m.off = wx - wx_al; m.predx = pred.x; m.predy = pred.y;
         m.valid = valid; m.band = band; m.bslot = lb % kBlockSlots; m.gblk = gblk;
         s_meta[stage] = m;
         if (valid) {
           uint8_t* st = smem + (size_t)stage * a.stage_bytes;
-          mbar_arrive_expect_tx(&s_full[stage], (uint32_t)(4 * a.box_bytes + a.blk_bytes));
-          const int wx = x2 - a.R, wy = y2 - a.R + band * a.band_rows;
-#pragma unroll
-          for (int s = 0; s < 4; ++s)
-            tma_load_3d(st + (size_t)s * a.copy_words * 4, &map_win, &s_full[stage], wx + s, wy - s * a.skew, pair);
-          tma_load_3d(st + (size_t)4 * a.copy_words * 4, &map_blk, &s_full[stage], bx * BS, by * BS, pair);
+          mbar_arrive_expect_tx(&s_full[stage], (uint32_t)(a.box_bytes + a.blk_bytes));
+          const int wy = y2 - a.R + band * a.band_rows;
+          tma_load_3d(st, &map_win, &s_full[stage], wx_al, wy, pair);
+          tma_load_3d(st + a.win_bytes, &map_blk, &s_full[stage], (bx * BS) & ~15, by * BS, pair);
         } else {
           mbar_arrive(&s_full[stage]);
         }
@@ -197,12 +199,13 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
         const bool active = q < items;
         const int qq = active ? q : 0;
         const int sidx = qq / a.n, o = qq - sidx * a.n;
-        const int sh = o & 3, wi = o >> 2;
+        const int bo = m.off + o;                 // byte column of this lane's displacement inside the staged box
+        const uint32_t sh = (uint32_t)(bo & 3) * 8u;
+        const int wi = bo >> 2;
         const int cy0 = sidx * SEG;
         const uint8_t* st = smem + (size_t)stage * a.stage_bytes;
-        const uint32_t* win = reinterpret_cast<const uint32_t*>(st) + (size_t)sh * a.copy_words +
-                              (size_t)(cy0 + sh * a.skew) * a.pww + wi;
-        const uint8_t* blk = st + (size_t)4 * a.copy_words * 4;
+        const uint32_t* win = reinterpret_cast<const uint32_t*>(st) + (size_t)cy0 * a.pww + wi;
+        const uint8_t* blk = st + a.win_bytes + (BS == 8 ? ((m.x2 - m.predx) & 8) : 0);
 
         uint32_t acc[SEG];
 #pragma unroll
@@ -226,10 +229,12 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
           const uint32_t* wb = win + (size_t)(qy * TW) * a.pww + qx * TWW;
 #pragma unroll
           for (int jr = 0; jr < SEG + TW - 1; ++jr) {
-            uint32_t wv[TWW];
+            uint32_t raw[TWW + 1], wv[TWW];
 #pragma unroll
-            for (int kk = 0; kk < TWW; ++kk) wv[kk] = wb[kk];
+            for (int kk = 0; kk <= TWW; ++kk) raw[kk] = wb[kk];
             wb += a.pww;
+#pragma unroll
+            for (int kk = 0; kk < TWW; ++kk) wv[kk] = __funnelshift_r(raw[kk], raw[kk + 1], sh);
 #pragma unroll
             for (int kk = 0; kk < TWW; ++kk) {
 #pragma unroll
@@ -365,27 +370,23 @@ static bool make_geom(int w, int h, int bs, int R, TmaGeom* g) {
   memset(g, 0, sizeof(*g));
   const int n = 2 * R + 1;
   const int seg = pick_seg(bs, R);
-  int words = ((2 * R) >> 2) + bs / 4;
-  int box_w = ((words * 4 + 15) / 16) * 16;
-  if ((box_w / 4) % 8 != 4) box_w += 16;  // row pitch == 4 (mod 8) words so that a row skew rotates banks by 8
+  // staged box: starts at the 16-byte aligned column at or below (x2 - R); a lane reads words
+  // (off + o) >> 2 ... + bs/4 inclusive, with off <= 15 and o <= 2R
+  const int words = ((15 + 2 * R) >> 2) + bs / 4 + 1;
+  const int box_w = ((words * 4 + 15) / 16) * 16;
   if (box_w > 256) return false;
-  const int pww = box_w / 4;
-  int skew = 0;
-  for (int m = 1; m < 8; ++m)
-    if ((m * pww) % 32 == 8) { skew = m; break; }
-  if (!skew) return false;
   const int segs_total = (n + seg - 1) / seg;
   const int blk_bytes = bs * (bs >= 16 ? bs : 16);
-  const size_t budget = 36 * 1024;  // per stage: kStages * 2 CTAs/SM must fit 227 KB
+  const size_t budget = 24 * 1024;  // per stage
   int spb = segs_total;
   for (;;) {
-    const int box_h = spb * seg + bs - 1 + 3 * skew;
-    const size_t copy_bytes = (((size_t)box_h * box_w) + 127) / 128 * 128;
-    const size_t stage = 4 * copy_bytes + ((blk_bytes + 127) / 128) * 128;
+    const int box_h = spb * seg + bs - 1;
+    const size_t win_bytes = (((size_t)box_h * box_w) + 127) / 128 * 128;
+    const size_t stage = win_bytes + ((blk_bytes + 127) / 128) * 128;
     if ((stage <= budget && box_h <= 256) || spb == 1) {
-      if (stage > 72 * 1024 || box_h > 256) return false;
+      if (stage > 64 * 1024 || box_h > 256) return false;
       g->box_h = box_h;
-      g->a.copy_words = (int)(copy_bytes / 4);
+      g->a.win_bytes = (int)win_bytes;
       g->a.stage_bytes = (int)stage;
       break;
     }
@@ -401,8 +402,7 @@ static bool make_geom(int w, int h, int bs, int R, TmaGeom* g) {
   g->a.nbands = (segs_total + spb - 1) / spb;
   g->a.band_rows = spb * seg;
   g->a.wi_max = (n * spb + 31) / 32;
-  g->a.pww = pww;
-  g->a.skew = skew;
+  g->a.pww = box_w / 4;
   g->a.box_bytes = g->box_h * box_w;
   g->a.blk_bytes = blk_bytes;
   g->smem = (size_t)kStages * g->a.stage_bytes;
@@ -411,11 +411,7 @@ static bool make_geom(int w, int h, int bs, int R, TmaGeom* g) {
 
 template <int BS, int SEG>
 static void launch_inst(const TmaSearchPlan& plan, const TmaSearchArgs& a, int grid, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(k_search_tma<BS, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    configured = true;
-  }
+  cudaFuncSetAttribute(k_search_tma<BS, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   k_search_tma<BS, SEG><<<grid, kThreads, plan.smem_bytes, s>>>(plan.map_win, plan.map_blk, a);
 }
 

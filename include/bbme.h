@@ -67,6 +67,8 @@ typedef struct {
   uint32_t kernel_launches;
   uint32_t fix_rounds;     /* total fixed-point rounds after the first full sweep pass */
   uint32_t fix_blocks;     /* blocks re-evaluated in those rounds */
+  uint32_t search_kernel_used; /* bbme_stage_search only: 1 = generic kernel ran, 2 = TMA kernel ran */
+  uint32_t search_launches;    /* search-kernel launches behind ms_search */
   uint32_t reserved;
   uint64_t search_candidates; /* in-bounds candidate positions evaluated (== oracle search_sad_calls) */
   uint64_t search_absdiffs;   /* pixels |a-b| in the search (== oracle search_absdiffs) */
@@ -120,8 +122,16 @@ int bbme_estimate_device(bbme_ctx* ctx, int n, const uint8_t* d_im1, const uint8
 int bbme_estimate_device_compact(bbme_ctx* ctx, int n, const uint8_t* d_im1, const uint8_t* d_im2,
                                  size_t pitch_bytes, size_t plane_stride, int16_t* d_mv, size_t mv_plane_stride);
 
+/* Waits for all slots; with collect_stats it then folds the CUDA-event intervals and work counters of everything
+ * enqueued since the previous bbme_sync / bbme_estimate_batch into the stats. */
 int bbme_sync(bbme_ctx* ctx);
 int bbme_get_stats(bbme_ctx* ctx, bbme_stats* out);
+/* Run slot i on caller stream streams[i] (cudaStream_t handles, e.g. torch.cuda.Stream.cuda_stream) instead of
+ * the context's own streams, so that the caller can bracket the work with its own events.  n must equal `slots`. */
+int bbme_set_streams(bbme_ctx* ctx, int n, void* const* streams);
+/* Live micro-benchmark of the VABSDIFF4.U8.ACC issue rate on this device (register-only, dependence-free chains on
+ * every SM, ~1 ms): the integer roofline denominator, in |a-b| per second.  Also returns the SM clock it ran at. */
+int bbme_measure_int_peak(bbme_ctx* ctx, double* absdiff_per_s, double* sm_mhz);
 int bbme_get_shape(const bbme_ctx* ctx, bbme_shape* out);
 
 /* Pinned host memory for asynchronous copies. */

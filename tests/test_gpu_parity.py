@@ -1,0 +1,229 @@
+"""Parity of the CUDA path against the CPU oracle, through the C ABI (bit-exact: all integer work; the float32
+regularisation energy is reproduced un-fused, so the chosen vectors are compared exactly too)."""
+import numpy as np
+import pytest
+
+import blockbasedmotionestimation_b200 as bb
+from helpers import blocks_to_dense, dense_to_blocks, describe_diff, make_pair, mv2_to_dense
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------------------------------ single stages
+@pytest.mark.parametrize("shape", [(64, 64), (96, 128), (50, 70), (52, 76), (272, 480), (544, 960), (34, 38)])
+def test_pyrdown_matches_oracle(gpu, oracle, shape):
+    h, w = shape
+    src = np.random.default_rng(h * 1000 + w).integers(0, 256, (h, w)).astype(np.uint8)
+    got = gpu.stage_pyrdown(src)
+    want = oracle.pyrdown(src)
+    assert np.array_equal(got, want), describe_diff(got, want)
+
+
+def _search_case(gpu, oracle, h, w, bs, ss, kernel, seed, kind="textured", pred_mode="zero"):
+    f1, f2 = make_pair(h, w, seed, shift=(3, -2), max_patch_shift=5, kind=kind)
+    gh, gw = h // bs, w // bs
+    rng = np.random.default_rng(seed + 1)
+    if pred_mode == "zero":
+        pred = np.zeros((gh, gw, 2), np.int16)
+    elif pred_mode == "small":
+        pred = rng.integers(-6, 7, (gh, gw, 2)).astype(np.int16)
+    else:  # predictions that partly leave the image (motion_framework.cpp:304-310)
+        pred = rng.integers(-max(h, w) // 3, max(h, w) // 3 + 1, (gh, gw, 2)).astype(np.int16)
+    got, st = gpu.stage_search(f1, f2, bs, ss, pred, kernel=kernel)
+    want_dense, ost = oracle.search_level(f1, f2, bs, ss, blocks_to_dense(pred, bs, h, w))
+    want = dense_to_blocks(want_dense, bs)
+    assert np.array_equal(got, want), describe_diff(got, want)
+    assert st["search_candidates"] == ost["search_sad_calls"]
+    assert st["search_absdiffs"] == ost["search_absdiffs"]
+    return st
+
+
+@pytest.mark.parametrize("bs,ss", [(2, 6), (4, 12), (8, 16), (8, 17), (16, 24), (16, 48), (32, 64), (64, 72)])
+@pytest.mark.parametrize("pred_mode", ["zero", "small", "wild"])
+def test_search_generic_matches_oracle(gpu, oracle, bs, ss, pred_mode):
+    h, w = max(4 * bs, 64), max(6 * bs, 96)
+    st = _search_case(gpu, oracle, h, w, bs, ss, 1, 100 + bs + ss, pred_mode=pred_mode)
+    assert st["search_kernel_used"] == 1  # generic kernel ran
+
+
+@pytest.mark.parametrize("bs,ss", [(8, 16), (8, 10), (8, 34), (16, 24), (16, 26), (16, 48), (16, 80), (32, 64), (32, 40),
+                                   (8, 136)])
+@pytest.mark.parametrize("pred_mode", ["zero", "small", "wild"])
+def test_search_tma_matches_oracle(gpu, oracle, bs, ss, pred_mode):
+    h, w = max(5 * bs, 96), max(7 * bs, 160)
+    st = _search_case(gpu, oracle, h, w, bs, ss, 2, 200 + bs + ss, pred_mode=pred_mode)
+    assert st["search_kernel_used"] == 2  # TMA kernel ran
+
+
+@pytest.mark.parametrize("kind", ["constant", "noise"])
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_search_tie_break_and_noise(gpu, oracle, kind, kernel):
+    # constant frames: every SAD ties, the spiral's first in-bounds position must win
+    _search_case(gpu, oracle, 96, 160, 16, 48, kernel, 7, kind=kind, pred_mode="small")
+
+
+@pytest.mark.parametrize("bs", [2, 4, 8, 16, 32])
+@pytest.mark.parametrize("mult", [1, 2])
+def test_regularize_sweep_matches_inplace_raster(gpu, oracle, bs, mult):
+    h, w = max(6 * bs, 48), max(9 * bs, 64)
+    f1, f2 = make_pair(h, w, 300 + bs, shift=(2, 1), max_patch_shift=4)
+    rng = np.random.default_rng(bs * 10 + mult)
+    # a noisy field, so that a plain Jacobi sweep differs from the in-place raster sweep
+    mv = rng.integers(-5, 6, (h // bs, w // bs, 2)).astype(np.int16)
+    lam = float(bs // 2)
+    got, rounds = gpu.stage_regularize(f1, f2, bs, lam, mult, mv)
+    want = dense_to_blocks(oracle.regularize_sweep(f1, f2, bs, lam, mult, blocks_to_dense(mv, bs, h, w)), bs)
+    assert np.array_equal(got, want), describe_diff(got, want)
+    assert rounds >= 1  # the noisy field must have needed fix-up rounds, i.e. the raster dependency is exercised
+
+
+def test_regularize_out_of_bounds_candidates_and_ties(gpu, oracle):
+    h, w, bs = 64, 96, 8
+    f = np.full((h, w), 77, np.uint8)  # all SADs tie at 0: smoothness and candidate order decide
+    rng = np.random.default_rng(5)
+    mv = rng.integers(-40, 41, (h // bs, w // bs, 2)).astype(np.int16)  # many candidates leave the image -> FLT_MAX
+    got, _ = gpu.stage_regularize(f, f, bs, 4.0, 1, mv)
+    want = dense_to_blocks(oracle.regularize_sweep(f, f, bs, 4.0, 1, blocks_to_dense(mv, bs, h, w)), bs)
+    assert np.array_equal(got, want), describe_diff(got, want)
+
+
+def test_divide_and_copy_mvs(gpu, oracle):
+    rng = np.random.default_rng(9)
+    mv = rng.integers(-30, 31, (6, 10, 2)).astype(np.int16)
+    got = gpu.stage_divide(mv)
+    want = dense_to_blocks(oracle.divide_blocks(blocks_to_dense(mv, 8, 48, 80), 8), 4)
+    assert np.array_equal(got, want)
+    for cbs, fbs in [(8, 8), (4, 16), (16, 4), (2, 2), (8, 2)]:
+        ch, cw = 64, 96
+        mv2 = rng.integers(-50, 51, (ch // 2, cw // 2, 2)).astype(np.int16)
+        got = gpu.stage_copy_mvs(mv2, cbs, fbs)
+        fine = oracle.copy_mvs(mv2_to_dense(mv2), cbs)
+        want = dense_to_blocks(fine, fbs)
+        assert np.array_equal(got, want), (cbs, fbs, describe_diff(got, want))
+
+
+# ------------------------------------------------------------------------------------------ whole path
+E2E_CASES = [
+    # h, w, search_size, block_size, sweeps, kind
+    (96, 128, [16, 16], [8, 8], 2, "textured"),
+    (90, 122, [20, 20, 20], [8, 8, 8], 2, "textured"),      # padded (3,3)
+    (192, 256, [48, 48, 48], [16, 16, 16], 2, "textured"),
+    (256, 320, [64, 64], [32, 32], 2, "textured"),
+    (128, 160, [24, 40], [8, 16], 2, "textured"),           # mixed block sizes across levels
+    (120, 200, [14, 12], [4, 4], 2, "noise"),
+    (64, 96, [6, 6], [2, 2], 2, "noise"),
+    (96, 128, [16, 16], [8, 8], 2, "constant"),
+    (192, 256, [48, 48, 48], [16, 16, 16], 5, "textured"),  # 5 sweeps (BASELINE config 5)
+    (100, 140, [17, 9], [8, 8], 1, "textured"),             # odd search_size - block_size, 1 sweep
+    (96, 128, [16, 16], [8, 8], 0, "textured"),             # no regularisation at all
+]
+
+
+@pytest.mark.parametrize("case", E2E_CASES)
+@pytest.mark.parametrize("search_kernel", [0, 1])
+def test_end_to_end_matches_oracle(oracle, case, search_kernel):
+    h, w, ss, bs, sweeps, kind = case
+    f1, f2 = make_pair(h, w, h * 7 + w, shift=(3, -2), max_patch_shift=6, kind=kind)
+    want, ost, dbg = oracle.estimate(f1, f2, ss, bs, sweeps, debug=True)
+    with bb.Estimator(w, h, ss, bs, sweeps=sweeps, search_kernel=search_kernel, collect_stats=True, keep_search_mv=True) as est:
+        got = est.estimate(f1, f2)
+        st = est.stats()
+        for l in range(len(bs)):
+            for f, key in ((0, "pyr1"), (1, "pyr2")):
+                img = est.level_image(l, f)
+                assert np.array_equal(img, dbg[key][l]), f"pyramid level {l} frame {f}: " + describe_diff(img, dbg[key][l])
+        for l in reversed(range(len(bs))):
+            a = est.level_mv(l, which=1)
+            b = dense_to_blocks(dbg["after_search"][l], bs[l])
+            assert np.array_equal(a, b), f"after search, level {l}: " + describe_diff(a, b)
+            a = est.level_mv(l, which=0)
+            b = dense_to_blocks(dbg["after_reg"][l], 2)
+            assert np.array_equal(a, b), f"after regularisation, level {l}: " + describe_diff(a, b)
+    assert got.shape == want.shape
+    assert np.array_equal(got, want), describe_diff(got, want)
+    assert st["search_absdiffs"] == ost["search_absdiffs"]
+    assert st["search_candidates"] == ost["search_sad_calls"]
+
+
+def test_mf_class_mirror(oracle):
+    """The reference-shaped entry point: MF(image1, image2, search_size, block_size, num_levels)."""
+    f1, f2 = make_pair(90, 122, 11)
+    ss, bs = [20, 20, 20], [8, 8, 8]
+    mf = bb.MF(f1, f2, ss, bs, 3)
+    flow = mf.calcMotionBlockMatching()
+    want, _ = oracle.estimate(f1, f2, ss, bs, 2)
+    assert (mf.padded_height, mf.padded_width, mf.padding_x, mf.padding_y) == (96, 128, 3, 3)
+    assert np.array_equal(flow, want)
+    mf.close()
+
+
+def test_batch_chunks_and_slots(oracle):
+    h, w, ss, bs = 96, 128, [16, 16], [8, 8]
+    pairs = [make_pair(h, w, 500 + i, shift=(i % 5 - 2, i % 3 - 1)) for i in range(7)]
+    with bb.Estimator(w, h, ss, bs, chunk_pairs=3, slots=2) as est:
+        flows = est.estimate_batch([p[0] for p in pairs], [p[1] for p in pairs])
+        flows2 = est.estimate_batch([p[0] for p in pairs[:2]], [p[1] for p in pairs[:2]])  # context reuse
+    for i, p in enumerate(pairs):
+        want, _ = oracle.estimate(p[0], p[1], ss, bs, 2)
+        assert np.array_equal(flows[i], want), f"pair {i}: " + describe_diff(flows[i], want)
+    assert np.array_equal(flows2[1], flows[1])
+
+
+def test_strided_input_rows(oracle):
+    h, w, ss, bs = 96, 128, [16, 16], [8, 8]
+    f1, f2 = make_pair(h, w, 21)
+    big1 = np.zeros((h, w + 37), np.uint8)
+    big2 = np.zeros((h, w + 37), np.uint8)
+    big1[:, :w] = f1
+    big2[:, :w] = f2
+    with bb.Estimator(w, h, ss, bs) as est:
+        got = est.estimate(big1[:, :w], big2[:, :w])  # OpenCV ROI semantics: any row stride
+    want, _ = oracle.estimate(f1, f2, ss, bs, 2)
+    assert np.array_equal(got, want)
+
+
+def test_identical_frames_give_zero_field():
+    f1, _ = make_pair(192, 256, 3)
+    with bb.Estimator(256, 192, [48, 48], [16, 16]) as est:
+        flow = est.estimate(f1, f1.copy())
+    assert not flow.any()
+
+
+def test_plan_errors_are_loud():
+    with pytest.raises(bb.BbmeError):
+        bb.Estimator(100, 100, [12], [6])  # block size not a power of two
+    with pytest.raises(bb.BbmeError):
+        bb.Estimator(101, 96, [16], [8])  # odd padding difference
+    with pytest.raises(bb.BbmeError):
+        bb.Estimator(8, 96, [16], [8])  # one block on the x axis (reference reads out of bounds, motion_framework.cpp:475)
+    with bb.Estimator(96, 96, [16], [8]) as est:
+        with pytest.raises(bb.BbmeError):
+            est.estimate(np.zeros((96, 64), np.uint8), np.zeros((96, 64), np.uint8))
+
+
+# ------------------------------------------------------------------------------------------ full size (BASELINE configs)
+def test_config2_1080p_matches_oracle(oracle):
+    """BASELINE config 2: 1920x1080, 16x16 blocks, +-32 (search_size 80), 3 levels -- the oracle takes ~4 s."""
+    h, w, ss, bs = 1080, 1920, [80, 80, 80], [16, 16, 16]
+    f1, f2 = make_pair(h, w, 2001, patches=12, max_patch_shift=40)
+    want, ost = oracle.estimate(f1, f2, ss, bs, 2)
+    with bb.Estimator(w, h, ss, bs, collect_stats=True) as est:
+        got = est.estimate(f1, f2)
+        st = est.stats()
+    assert np.array_equal(got, want), describe_diff(got, want)
+    assert st["search_absdiffs"] == ost["search_absdiffs"]
+
+
+def test_config3_4k_properties():
+    """BASELINE config 3 (3840x2160, 8x8, +-64, 4 levels) is ~7 min on the oracle, so it is checked through
+    size-independent properties: a pure global shift is recovered in the interior, the field is 2x2-constant,
+    and the TMA kernel and the generic kernel agree on the coarsest two levels' geometry (cropped)."""
+    h, w, ss, bs = 2160, 3840, [136] * 4, [8] * 4
+    f1, f2 = make_pair(h, w, 3001, shift=(9, -7), patches=0, noise=0)
+    with bb.Estimator(w, h, ss, bs) as est:
+        flow = est.estimate(f1, f2)
+        py = est.shape["padding_y"]
+    assert np.array_equal(flow[0::2, 0::2], flow[1::2, 1::2])
+    inner = flow[py + 256:py + h - 256, 256:w - 256]
+    frac = np.mean((inner[..., 0] == -9) & (inner[..., 1] == 7))
+    assert frac > 0.999, frac
