@@ -56,6 +56,7 @@ SIGNATURES = {
     "bbme_plan": (_I, [_P, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(BbmeOptions), C.POINTER(BbmeShape)]),
     "bbme_estimate": (_I, [_P, _P, _P, _SZ, _P]),
     "bbme_estimate_batch": (_I, [_P, _I, C.POINTER(_P), C.POINTER(_P), _SZ, C.POINTER(_P)]),
+    "bbme_estimate_batch_async": (_I, [_P, _I, C.POINTER(_P), C.POINTER(_P), _SZ, C.POINTER(_P)]),
     "bbme_estimate_device": (_I, [_P, _I, _P, _P, _SZ, _SZ, _P, _SZ]),
     "bbme_estimate_device_compact": (_I, [_P, _I, _P, _P, _SZ, _SZ, _P, _SZ]),
     "bbme_sync": (_I, [_P]),

@@ -64,6 +64,8 @@ struct bbme_ctx {
   uint32_t launches = 0;
   uint32_t search_launches = 0;
   bool stats_armed = false;
+  int next_slot = 0;    // round-robin position over the slots across asynchronous calls
+  int grid_rounds = 3;  // fix-up rounds run grid-wide before the per-pair tail loop (BBME_GRID_ROUNDS)
 };
 
 namespace {
@@ -262,8 +264,9 @@ int run_chunk(bbme_ctx* c, Slot& s, int n, const uint8_t* d_in1, const uint8_t* 
         ra.wl_plane = c->cap[0];
         ra.ctr = s.ctr;
         launch_reg_full(ra, n, st);
-        launch_reg_fix(ra, n, st);
-        c->launches += 2;
+        for (int r = 0; r < c->grid_rounds; ++r) launch_reg_round(ra, r, n, st);
+        launch_reg_fix(ra, c->grid_rounds, n, st);
+        c->launches += 2 + c->grid_rounds;
         short2* t = cur; cur = nxt; nxt = t;
       }
       if (g > 2) {
@@ -308,6 +311,7 @@ int collect_after_sync(bbme_ctx* c) {
       for (int p = 0; p < s.last_n; ++p) {
         c->stats.fix_rounds += ctr[(size_t)p * kCtrWords + CTR_ROUNDS];
         c->stats.fix_blocks += ctr[(size_t)p * kCtrWords + CTR_BLOCKS];
+        c->stats.reserved += ctr[(size_t)p * kCtrWords + CTR_TAIL_BLOCKS];
       }
       s.last_n = 0;
     }
@@ -335,6 +339,7 @@ void begin_call(bbme_ctx* c) {
     s.last_n = 0;
     cudaMemsetAsync(s.counters, 0, 2 * sizeof(unsigned long long), s.stream);
     cudaMemset2DAsync(s.ctr + CTR_ROUNDS, kCtrWords * sizeof(uint32_t), 0, 2 * sizeof(uint32_t), c->opt.chunk_pairs, s.stream);
+    cudaMemset2DAsync(s.ctr + CTR_TAIL_BLOCKS, kCtrWords * sizeof(uint32_t), 0, sizeof(uint32_t), c->opt.chunk_pairs, s.stream);
   }
   c->stats_armed = true;
 }
@@ -395,6 +400,10 @@ int bbme_create(bbme_ctx** out, int device) {
   bbme_ctx* c = new bbme_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
+  if (const char* gr = getenv("BBME_GRID_ROUNDS")) {
+    const int v = atoi(gr);
+    if (v >= 0 && v <= 64) c->grid_rounds = v;
+  }
   bbme_default_options(&c->opt);
   *out = c;
   return BBME_OK;
@@ -524,8 +533,8 @@ int bbme_get_stats(bbme_ctx* c, bbme_stats* out) {
   return BBME_OK;
 }
 
-int bbme_estimate_batch(bbme_ctx* c, int n, const uint8_t* const* im1, const uint8_t* const* im2, size_t pitch,
-                        float* const* flow) {
+int bbme_estimate_batch_async(bbme_ctx* c, int n, const uint8_t* const* im1, const uint8_t* const* im2, size_t pitch,
+                              float* const* flow) {
   if (!c) return BBME_E_ARG;
   if (!c->planned) return fail(c, BBME_E_STATE, "bbme_estimate_batch before bbme_plan");
   if (n <= 0 || !im1 || !im2 || !flow || pitch < (size_t)c->shape.width) return fail(c, BBME_E_ARG, "bbme_estimate_batch: bad arguments");
@@ -535,7 +544,7 @@ int bbme_estimate_batch(bbme_ctx* c, int n, const uint8_t* const* im1, const uin
   begin_call(c);
   const int chunk = c->opt.chunk_pairs;
   const size_t flow_bytes = c->out_plane * sizeof(float);
-  int ci = 0;
+  int ci = c->next_slot;
   for (int start = 0; start < n; start += chunk, ++ci) {
     Slot& s = c->slots[ci % c->slots.size()];
     const int m = (n - start < chunk) ? (n - start) : chunk;
@@ -550,7 +559,15 @@ int bbme_estimate_batch(bbme_ctx* c, int n, const uint8_t* const* im1, const uin
     for (int i = 0; i < m; ++i)
       CUDA_TRY(c, cudaMemcpyAsync(flow[start + i], s.out + (size_t)i * c->out_plane, flow_bytes, cudaMemcpyDeviceToHost, s.stream));
   }
-  int rc = sync_all(c);
+  c->next_slot = ci % (int)c->slots.size();
+  return BBME_OK;
+}
+
+int bbme_estimate_batch(bbme_ctx* c, int n, const uint8_t* const* im1, const uint8_t* const* im2, size_t pitch,
+                        float* const* flow) {
+  int rc = bbme_estimate_batch_async(c, n, im1, im2, pitch, flow);
+  if (rc) return rc;
+  rc = sync_all(c);
   if (rc) return rc;
   return collect_after_sync(c);
 }
@@ -769,7 +786,8 @@ int bbme_stage_regularize(bbme_ctx* c, const uint8_t* im1, const uint8_t* im2, i
   ra.O = O; ra.Y = Y; ra.mv_plane = nb;
   ra.list0 = l0; ra.list1 = l1; ra.nv = nv; ra.stamp = stamp; ra.wl_plane = nb; ra.ctr = ctr;
   launch_reg_full(ra, 1, 0);
-  launch_reg_fix(ra, 1, 0);
+  for (int r = 0; r < c->grid_rounds; ++r) launch_reg_round(ra, r, 1, 0);
+  launch_reg_fix(ra, c->grid_rounds, 1, 0);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return fail(c, BBME_E_CUDA, "stage_regularize kernel failed: %s", cudaGetErrorString(e));
   CUDA_TRY(c, cudaMemcpy(mv, Y, nb * sizeof(short2), cudaMemcpyDeviceToHost));

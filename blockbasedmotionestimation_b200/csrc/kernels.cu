@@ -291,8 +291,124 @@ void launch_export_compact(const short2* mv2, int gw2, int gh2, size_t mv_plane,
 //
 // Energy (:607) is float32 and un-fused: (float)SAD + ((lambda * (float)mult) * S); S is a sum of
 // integer-valued floats (< 2^24, exact), so it is accumulated in int and converted once.
+//
+// Small blocks (2x2, 4x4: 95 % of all block evaluations) are evaluated by one thread, branch-free: all nine slots
+// are always computed (missing neighbours hold a copy of C and are masked out of the argmin; their contribution to
+// the smoothness sums is removed arithmetically), so a warp never diverges; the only branch is warp-uniform (every
+// lane's nine candidates identical -> nothing can change).
+template <int BS>  // 2 or 4
+__device__ __forceinline__ short2 reg_eval_small(const RegArgs& a, int pair, const short2* __restrict__ O,
+                                                 const short2* P, int bx, int by, bool live) {
+  const int gw = a.gw, gh = a.gh;
+  const int idx = by * gw + bx;
+  const bool up = by > 0, dn = by < gh - 1, lf = bx > 0, rt = bx < gw - 1;
+  const short2 c0 = O[idx];
+  short2 c[9];
+  c[0] = c0;
+  c[1] = lf ? P[idx - 1] : c0;
+  c[2] = rt ? O[idx + 1] : c0;
+  c[3] = (dn && rt) ? O[idx + gw + 1] : c0;
+  c[4] = (up && lf) ? P[idx - gw - 1] : c0;
+  c[5] = (up && rt) ? P[idx - gw + 1] : c0;
+  c[6] = up ? P[idx - gw] : c0;
+  c[7] = dn ? O[idx + gw] : c0;
+  c[8] = (dn && lf) ? O[idx + gw - 1] : c0;
+  const uint32_t k0 = pack_mv(c0);
+  bool all_same = true;
+#pragma unroll
+  for (int i = 1; i < 9; ++i) all_same = all_same && (pack_mv(c[i]) == k0);
+  // warp-uniform early out: identical candidates have identical energies, index 0 wins (:653-659)
+  if (__all_sync(__activemask(), all_same || !live)) return c0;
+
+  const uint32_t vmask = 1u | (lf ? 2u : 0u) | (rt ? 4u : 0u) | ((dn && rt) ? 8u : 0u) | ((up && lf) ? 16u : 0u) |
+                         ((up && rt) ? 32u : 0u) | (up ? 64u : 0u) | (dn ? 128u : 0u) | ((dn && lf) ? 256u : 0u);
+  const float n_missing = (float)(9 - __popc(vmask));
+  int cx[9], cy[9];
+  float fx[9], fy[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    cx[i] = c[i].x; cy[i] = c[i].y;
+    fx[i] = (float)cx[i]; fy[i] = (float)cy[i];
+  }
+  // S_i over the gathered candidates (:637-641), accumulated in float like the reference (integer-valued, exact):
+  // |a - b| + acc is FADD + FADD-with-|.|-modifier on the FMA pipe.  Sum over all nine slots, then remove the
+  // missing slots' share (each holds C, i.e. contributes d(i, 0)).
+  float S[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) S[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+#pragma unroll
+    for (int k = i + 1; k < 9; ++k) {
+      const float d = __fadd_rn(fabsf(__fsub_rn(fx[i], fx[k])), fabsf(__fsub_rn(fy[i], fy[k])));
+      S[i] = __fadd_rn(S[i], d);
+      S[k] = __fadd_rn(S[k], d);
+    }
+  }
+  {
+    // d(i, 0) for the correction; S[0] needs none (d(0,0) = 0)
+#pragma unroll
+    for (int i = 1; i < 9; ++i) {
+      const float d0 = __fadd_rn(fabsf(__fsub_rn(fx[i], fx[0])), fabsf(__fsub_rn(fy[i], fy[0])));
+      S[i] = __fmaf_rn(-n_missing, d0, S[i]);
+    }
+  }
+
+  const int x = bx * BS, y = by * BS;
+  const int w = a.i1.w, h = a.i1.h, pitch = a.i1.pitch;
+  const uint8_t* blk = a.i1.p + (size_t)pair * a.i1.plane + (size_t)y * pitch + x;
+  const uint8_t* ref = a.i2.p + (size_t)pair * a.i2.plane;
+  uint32_t A[BS == 2 ? 1 : 4];
+  if (BS == 2) {
+    A[0] = (uint32_t)*reinterpret_cast<const uint16_t*>(blk) | ((uint32_t)*reinterpret_cast<const uint16_t*>(blk + pitch) << 16);
+  } else {
+#pragma unroll
+    for (int r = 0; r < (BS == 2 ? 1 : 4); ++r) A[r] = *reinterpret_cast<const uint32_t*>(blk + (size_t)r * pitch);
+  }
+  float best = 0.f;
+  int best_i = 0;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const int px = x + cx[i], py = y + cy[i];
+    const bool inb = (unsigned)px <= (unsigned)(w - BS) && (unsigned)py <= (unsigned)(h - BS);  // :578
+    const uint8_t* b = ref + (size_t)(inb ? py : y) * pitch + (inb ? px : x);  // out-of-image candidates read the block's own position
+    uint32_t sad;
+    if (BS == 2) {
+      const uint32_t bv = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[pitch] << 16) | ((uint32_t)b[pitch + 1] << 24);
+      sad = sad4(A[0], bv, 0u);
+    } else {
+      sad = 0;
+      const uintptr_t ab = reinterpret_cast<uintptr_t>(b);
+      const uint32_t sh = (uint32_t)(ab & 3) * 8u;
+      const uint32_t* bw = reinterpret_cast<const uint32_t*>(ab & ~(uintptr_t)3);
+#pragma unroll
+      for (int r = 0; r < (BS == 2 ? 1 : 4); ++r) {
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(bw) + (size_t)r * pitch);
+        sad = sad4(A[r], __funnelshift_r(rw[0], rw[1], sh), sad);
+      }
+    }
+    const float e = inb ? __fadd_rn(__uint2float_rn(sad), __fmul_rn(a.lm, S[i])) : FLT_MAX;
+    if (i == 0) {
+      best = e;
+    } else {
+      const bool take = ((vmask >> i) & 1u) && (e < best);
+      best = take ? e : best;
+      best_i = take ? i : best_i;
+    }
+  }
+  short2 r = c0;
+#pragma unroll
+  for (int i = 1; i < 9; ++i) r = (best_i == i) ? c[i] : r;
+  return r;
+}
+
+//
+// A block is evaluated by a TEAM of adjacent lanes (1 for block sizes 2 and 4, min(bs, 32) above): every lane takes
+// bs / TEAM rows of each candidate's SAD and the partial sums are combined with xor-shuffles inside the team, so
+// the latency of one evaluation no longer grows with the block area (the fix-up rounds are latency-bound).
+template <int TEAM>
 __device__ __forceinline__ short2 reg_eval(const RegArgs& a, int pair, const short2* __restrict__ O,
-                                           const short2* P, int bx, int by) {
+                                           const short2* P, int bx, int by, int tl, uint32_t team_mask) {
   const int gw = a.gw, gh = a.gh, bs = a.bs;
   const int idx = by * gw + bx;
   const bool up = by > 0, dn = by < gh - 1, lf = bx > 0, rt = bx < gw - 1;
@@ -336,6 +452,8 @@ __device__ __forceinline__ short2 reg_eval(const RegArgs& a, int pair, const sho
   const int w = a.i1.w, h = a.i1.h, pitch = a.i1.pitch;
   const uint8_t* blk = a.i1.p + (size_t)pair * a.i1.plane + (size_t)y * pitch + x;
   const uint8_t* ref = a.i2.p + (size_t)pair * a.i2.plane;
+  const int rows = TEAM > 1 ? bs / TEAM : bs;  // rows of the block this lane sums
+  const int r0 = TEAM > 1 ? tl * rows : 0;
   float best = 0.f;
   int best_i = 0;
 #pragma unroll
@@ -351,7 +469,27 @@ __device__ __forceinline__ short2 reg_eval(const RegArgs& a, int pair, const sho
     if (px < 0 || px > w - bs || py < 0 || py > h - bs) {
       e = FLT_MAX;  // :578-582
     } else {
-      const uint32_t sad = sad_block_unaligned(blk, ref + (size_t)py * pitch + px, pitch, bs);
+      uint32_t sad;
+      if (TEAM == 1) {
+        sad = sad_block_unaligned(blk, ref + (size_t)py * pitch + px, pitch, bs);
+      } else {
+        sad = 0;
+        const int words = bs >> 2;
+        for (int r = r0; r < r0 + rows; ++r) {
+          const uint32_t* aw = reinterpret_cast<const uint32_t*>(blk + (size_t)r * pitch);
+          const uintptr_t ab = reinterpret_cast<uintptr_t>(ref + (size_t)(py + r) * pitch + px);
+          const uint32_t* bw = reinterpret_cast<const uint32_t*>(ab & ~(uintptr_t)3);
+          const uint32_t sh = (uint32_t)(ab & 3) * 8u;
+          uint32_t w0 = __ldg(bw);
+          for (int k = 0; k < words; ++k) {
+            const uint32_t w1 = __ldg(bw + k + 1);
+            sad = sad4(__ldg(aw + k), __funnelshift_r(w0, w1, sh), sad);
+            w0 = w1;
+          }
+        }
+#pragma unroll
+        for (int off = TEAM / 2; off > 0; off >>= 1) sad += __shfl_xor_sync(team_mask, sad, off);
+      }
       e = __fadd_rn(__uint2float_rn(sad), __fmul_rn(a.lm, __int2float_rn(S[i])));
     }
     if (i == 0) { best = e; best_i = 0; }
@@ -374,17 +512,40 @@ __device__ __forceinline__ void for_each_dependent(int bx, int by, int gw, int g
   }
 }
 
+// TEAM == 1 evaluates 2x2 blocks, TEAM == 2 is the tag for "one thread per 4x4 block" (TEAMSZ below is 1 for both)
+template <int TEAM>
+__device__ __forceinline__ short2 reg_eval_any(const RegArgs& a, int pair, const short2* __restrict__ O, const short2* P,
+                                               int bx, int by, int tl, uint32_t team_mask, bool live) {
+  if (TEAM == 1) {
+    return reg_eval_small<2>(a, pair, O, P, bx, by, live);
+  } else if (TEAM == 2) {
+    return reg_eval_small<4>(a, pair, O, P, bx, by, live);
+  } else {
+    return reg_eval<TEAM>(a, pair, O, P, bx, by, tl, team_mask);
+  }
+}
+
 // Pass 1 of a sweep: every block evaluated with the OLD field for all nine slots (a Jacobi step).  Blocks
 // whose value changed enqueue their dependents: those may have used a stale "pred" value.
-__global__ void __launch_bounds__(256) k_reg_full(RegArgs a) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+template <int TEAM>
+__global__ void __launch_bounds__(128, TEAM <= 2 ? 4 : 1) k_reg_full(RegArgs a) {
+  constexpr int TEAMSZ = TEAM <= 2 ? 1 : TEAM;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int i = t / TEAMSZ;
+  const int tl = t % TEAMSZ;
   const int pair = blockIdx.y;
-  if (i >= a.gw * a.gh) return;
+  const bool live = i < a.gw * a.gh;
+  if (!live) {
+    if (TEAMSZ > 1) return;  // whole teams leave together (blockDim is a multiple of TEAM)
+    i = a.gw * a.gh - 1;     // one thread per block: keep the warp converged for the warp-uniform early-out
+  }
+  const uint32_t team_mask = TEAMSZ >= 32 ? 0xffffffffu : (((1u << TEAMSZ) - 1u) << ((threadIdx.x & 31) / TEAMSZ * TEAMSZ));
   const int bx = i % a.gw, by = i / a.gw;
   const short2* O = a.O + (size_t)pair * a.mv_plane;
   short2* Y = a.Y + (size_t)pair * a.mv_plane;
   uint32_t* ctr = a.ctr + (size_t)pair * kCtrWords;
-  const short2 nv = reg_eval(a, pair, O, O, bx, by);
+  const short2 nv = reg_eval_any<TEAM>(a, pair, O, O, bx, by, tl, team_mask, live);
+  if (tl != 0 || !live) return;
   Y[i] = nv;
   if (pack_mv(nv) != pack_mv(O[i])) {
     const uint32_t ep = ctr[CTR_EPOCH] + 1u;
@@ -396,46 +557,95 @@ __global__ void __launch_bounds__(256) k_reg_full(RegArgs a) {
   }
 }
 
-// Passes 2..: one CTA per pair iterates Jacobi rounds on the active set until nothing changes.  The update
-// map is triangular in raster order (a block depends on earlier blocks' NEW values and later blocks' OLD
-// values only), so the fixed point is unique and equals the reference's in-place raster sweep.
-__global__ void __launch_bounds__(1024) k_reg_fix(RegArgs a) {
+// Passes 2..: rounds on the active set until nothing changes.  The update map is triangular in raster order (a
+// block depends on earlier blocks' NEW values and later blocks' OLD values only), so the fixed point is unique and
+// equals the reference's in-place raster sweep.  Rounds update Y in place ("chaotic" iteration): an evaluation may
+// read a neighbour before or after that neighbour's update of the same round; whenever a block changes, its
+// dependents are (re-)enqueued for the next round, so a block that read a stale value is always evaluated again
+// after the next barrier / kernel boundary.  Only the path to the fixed point varies, not the result.
+//
+// Round r reads list[r & 1] (count in counter r % 3), appends to list[(r + 1) & 1] (counter (r + 1) % 3, stamp
+// epoch + 2 + r) and clears counter (r + 2) % 3 for the round after.  The first rounds are the big ones and run as
+// grid-wide kernels over all pairs (k_reg_round); the tail, where rounds are short and latency-bound, runs as one
+// CTA per pair that loops until its list is empty (k_reg_fix).
+__device__ __forceinline__ int ctr_index(int k) { return k == 2 ? CTR_COUNT2 : k; }
+
+template <int TEAM>
+__global__ void __launch_bounds__(256, TEAM <= 2 ? 2 : 1) k_reg_round(RegArgs a, int r) {
+  constexpr int TEAMSZ = TEAM <= 2 ? 1 : TEAM;
+  const int pair = blockIdx.y;
+  uint32_t* ctr = a.ctr + (size_t)pair * kCtrWords;
+  const uint32_t cnt = ctr[ctr_index(r % 3)];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    ctr[ctr_index((r + 2) % 3)] = 0;
+    if (cnt) { ctr[CTR_ROUNDS] += 1; ctr[CTR_BLOCKS] += cnt; }
+  }
+  if (cnt == 0) return;
+  const short2* O = a.O + (size_t)pair * a.mv_plane;
+  short2* Y = a.Y + (size_t)pair * a.mv_plane;
+  uint32_t* stamp = a.stamp + (size_t)pair * a.wl_plane;
+  const uint32_t* lc = ((r & 1) ? a.list1 : a.list0) + (size_t)pair * a.wl_plane;
+  uint32_t* ln = ((r & 1) ? a.list0 : a.list1) + (size_t)pair * a.wl_plane;
+  uint32_t* next_count = &ctr[ctr_index((r + 1) % 3)];
+  const uint32_t ep = ctr[CTR_EPOCH] + 2u + (uint32_t)r;
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t team = gtid / TEAMSZ, tl = gtid % TEAMSZ, nteams = gridDim.x * blockDim.x / TEAMSZ;
+  const uint32_t team_mask = TEAMSZ >= 32 ? 0xffffffffu : (((1u << TEAMSZ) - 1u) << ((threadIdx.x & 31) / TEAMSZ * TEAMSZ));
+  const uint32_t limit = TEAMSZ == 1 ? ((cnt + 31u) & ~31u) : cnt;
+  for (uint32_t e = team; e < limit; e += nteams) {
+    const bool live = e < cnt;
+    const int b = (int)lc[live ? e : cnt - 1];
+    const int bx = b % a.gw, by = b / a.gw;
+    const short2 nv = reg_eval_any<TEAM>(a, pair, O, Y, bx, by, (int)tl, team_mask, live);
+    if (tl == 0 && live && pack_mv(nv) != pack_mv(Y[b])) {
+      Y[b] = nv;
+      for_each_dependent(bx, by, a.gw, a.gh, [&](int d) {
+        if (atomicExch(&stamp[d], ep) != ep) ln[atomicAdd(next_count, 1u)] = (uint32_t)d;
+      });
+    }
+  }
+}
+
+template <int TEAM>
+__global__ void __launch_bounds__(TEAM <= 2 ? 512 : 1024) k_reg_fix(RegArgs a, int r0) {
+  constexpr int TEAMSZ = TEAM <= 2 ? 1 : TEAM;
   const int pair = blockIdx.x;
   const short2* O = a.O + (size_t)pair * a.mv_plane;
   short2* Y = a.Y + (size_t)pair * a.mv_plane;
   uint32_t* ctr = a.ctr + (size_t)pair * kCtrWords;
   uint32_t* stamp = a.stamp + (size_t)pair * a.wl_plane;
   uint32_t* lists[2] = {a.list0 + (size_t)pair * a.wl_plane, a.list1 + (size_t)pair * a.wl_plane};
-  short2* nvb = a.nv + (size_t)pair * a.wl_plane;
-  __shared__ uint32_t s_next;
-  uint32_t cnt = ctr[CTR_COUNT0];
-  if (cnt == 0) return;  // the Jacobi pass was already the raster result
-  uint32_t ep = ctr[CTR_EPOCH] + 1u;
+  __shared__ uint32_t s_next[2];
+  uint32_t cnt = ctr[ctr_index(r0 % 3)];
+  uint32_t ep = ctr[CTR_EPOCH] + 1u + (uint32_t)r0;  // appends of round r use ep + 1 = epoch + 2 + r
+  const uint32_t team = threadIdx.x / TEAMSZ, tl = threadIdx.x % TEAMSZ, nteams = blockDim.x / TEAMSZ;
+  const uint32_t team_mask = TEAMSZ >= 32 ? 0xffffffffu : (((1u << TEAMSZ) - 1u) << ((threadIdx.x & 31) / TEAMSZ * TEAMSZ));
   uint32_t rounds = 0, blocks = 0;
-  int cur = 0;
+  int cur = r0 & 1;
+  if (threadIdx.x == 0) { s_next[0] = 0; s_next[1] = 0; }
+  __syncthreads();
   while (cnt > 0) {
-    if (threadIdx.x == 0) s_next = 0;
-    __syncthreads();
     const uint32_t* lc = lists[cur];
     uint32_t* ln = lists[cur ^ 1];
-    for (uint32_t e = threadIdx.x; e < cnt; e += blockDim.x) {
-      const int b = (int)lc[e];
-      nvb[e] = reg_eval(a, pair, O, Y, b % a.gw, b / a.gw);
-    }
-    __syncthreads();
-    for (uint32_t e = threadIdx.x; e < cnt; e += blockDim.x) {
-      const int b = (int)lc[e];
-      const short2 nv = nvb[e];
-      if (pack_mv(nv) != pack_mv(Y[b])) {
+    uint32_t* next_count = &s_next[cur ^ 1];
+    // one thread per block: whole warps iterate together (the evaluator's early-out is warp-uniform)
+    const uint32_t limit = TEAMSZ == 1 ? ((cnt + 31u) & ~31u) : cnt;
+    for (uint32_t e = team; e < limit; e += nteams) {
+      const bool live = e < cnt;
+      const int b = (int)lc[live ? e : cnt - 1];
+      const int bx = b % a.gw, by = b / a.gw;
+      const short2 nv = reg_eval_any<TEAM>(a, pair, O, Y, bx, by, (int)tl, team_mask, live);
+      if (tl == 0 && live && pack_mv(nv) != pack_mv(Y[b])) {
         Y[b] = nv;
-        for_each_dependent(b % a.gw, b / a.gw, a.gw, a.gh, [&](int d) {
-          if (atomicExch(&stamp[d], ep + 1u) != ep + 1u) ln[atomicAdd(&s_next, 1u)] = (uint32_t)d;
+        for_each_dependent(bx, by, a.gw, a.gh, [&](int d) {
+          if (atomicExch(&stamp[d], ep + 1u) != ep + 1u) ln[atomicAdd(next_count, 1u)] = (uint32_t)d;
         });
       }
     }
     __syncthreads();
     blocks += cnt;
-    cnt = s_next;
+    cnt = *next_count;
+    if (threadIdx.x == 0) s_next[cur] = 0;  // becomes the append counter of the round after next
     cur ^= 1;
     ++ep;
     ++rounds;
@@ -444,19 +654,55 @@ __global__ void __launch_bounds__(1024) k_reg_fix(RegArgs a) {
   if (threadIdx.x == 0) {
     ctr[CTR_COUNT0] = 0;
     ctr[CTR_COUNT1] = 0;
+    ctr[CTR_COUNT2] = 0;
     ctr[CTR_EPOCH] = ep;
     ctr[CTR_ROUNDS] += rounds;
     ctr[CTR_BLOCKS] += blocks;
+    ctr[CTR_TAIL_BLOCKS] += blocks;
   }
 }
 
+// evaluator variant per block size: 1 = one thread per 2x2 block, 2 = one thread per 4x4 block, else lanes per block
+static int team_for(int bs) { return bs >= 32 ? 32 : (bs >= 8 ? bs : (bs == 4 ? 2 : 1)); }
+
 void launch_reg_full(const RegArgs& a, int n, cudaStream_t s) {
-  dim3 grid((a.gw * a.gh + 127) / 128, n);
-  k_reg_full<<<grid, 128, 0, s>>>(a);
+  const int team = team_for(a.bs);
+  const int lanes = team <= 2 ? 1 : team;
+  dim3 grid((unsigned)(((size_t)a.gw * a.gh * lanes + 127) / 128), n);
+  switch (team) {
+    case 32: k_reg_full<32><<<grid, 128, 0, s>>>(a); break;
+    case 16: k_reg_full<16><<<grid, 128, 0, s>>>(a); break;
+    case 8: k_reg_full<8><<<grid, 128, 0, s>>>(a); break;
+    case 2: k_reg_full<2><<<grid, 128, 0, s>>>(a); break;
+    default: k_reg_full<1><<<grid, 128, 0, s>>>(a); break;
+  }
 }
 
-void launch_reg_fix(const RegArgs& a, int n, cudaStream_t s) { k_reg_fix<<<n, 1024, 0, s>>>(a); }
+void launch_reg_round(const RegArgs& a, int r, int n, cudaStream_t s) {
+  const int team = team_for(a.bs);
+  const int lanes = team <= 2 ? 1 : team;
+  // enough CTAs per pair to spread a few-percent active set of this grid over the chip, at most 16
+  size_t want = ((size_t)a.gw * a.gh * lanes / 16 + 255) / 256;
+  unsigned bx = (unsigned)(want < 1 ? 1 : (want > 16 ? 16 : want));
+  dim3 grid(bx, n);
+  switch (team) {
+    case 32: k_reg_round<32><<<grid, 256, 0, s>>>(a, r); break;
+    case 16: k_reg_round<16><<<grid, 256, 0, s>>>(a, r); break;
+    case 8: k_reg_round<8><<<grid, 256, 0, s>>>(a, r); break;
+    case 2: k_reg_round<2><<<grid, 256, 0, s>>>(a, r); break;
+    default: k_reg_round<1><<<grid, 256, 0, s>>>(a, r); break;
+  }
+}
 
+void launch_reg_fix(const RegArgs& a, int r0, int n, cudaStream_t s) {
+  switch (team_for(a.bs)) {
+    case 32: k_reg_fix<32><<<n, 1024, 0, s>>>(a, r0); break;
+    case 16: k_reg_fix<16><<<n, 1024, 0, s>>>(a, r0); break;
+    case 8: k_reg_fix<8><<<n, 1024, 0, s>>>(a, r0); break;
+    case 2: k_reg_fix<2><<<n, 512, 0, s>>>(a, r0); break;
+    default: k_reg_fix<1><<<n, 512, 0, s>>>(a, r0); break;
+  }
+}
 
 // ============================================================================================ integer peak
 // Register-only, dependence-free VABSDIFF4.U8.ACC chains on every SM (same measurement as bench_micro/int_peak.cu).

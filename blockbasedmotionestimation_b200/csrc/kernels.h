@@ -10,7 +10,7 @@ namespace bbme {
 
 // per-pair control words of the regularisation fix-up (device memory, kCtrWords uint32 per pair)
 constexpr int kCtrWords = 8;
-enum { CTR_COUNT0 = 0, CTR_COUNT1 = 1, CTR_EPOCH = 2, CTR_ROUNDS = 3, CTR_BLOCKS = 4 };
+enum { CTR_COUNT0 = 0, CTR_COUNT1 = 1, CTR_EPOCH = 2, CTR_ROUNDS = 3, CTR_BLOCKS = 4, CTR_COUNT2 = 5, CTR_TAIL_BLOCKS = 6 };
 
 struct RegArgs {
   ImgView i1, i2;
@@ -51,7 +51,9 @@ void launch_export_compact(const short2* mv2, int gw2, int gh2, size_t mv_plane,
                            cudaStream_t s);
 // one regularisation sweep = full Jacobi pass + per-pair fixed-point rounds (exactly the in-place raster result)
 void launch_reg_full(const RegArgs& a, int n, cudaStream_t s);
-void launch_reg_fix(const RegArgs& a, int n, cudaStream_t s);
+// grid-wide fix-up round `r` (0-based) over all pairs; then the per-pair tail loop starting at round `r0`
+void launch_reg_round(const RegArgs& a, int r, int n, cudaStream_t s);
+void launch_reg_fix(const RegArgs& a, int r0, int n, cudaStream_t s);
 
 // VABSDIFF4 issue-rate micro-benchmark (kernels.cu); returns 0 on success
 int measure_int_peak(int sm_count, double* absdiff_per_s, double* sm_mhz);

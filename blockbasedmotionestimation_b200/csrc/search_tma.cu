@@ -17,7 +17,9 @@
 //    (16) registers, SEG accumulators in registers, every window word loaded once per lane feeds up to 16 SADs.
 //  * The 32 lanes of a work item take consecutive dx, i.e. consecutive bytes: 8-9 distinct consecutive words per
 //    shared load, conflict-free.
-//  * Block results are reduced with a 64-bit (SAD, spiral rank) key: warp shuffle -> shared atomicMin.
+//  * Block results are reduced with a 32-bit key (SAD << KS | spiral rank); the ranks come from a table built once
+//    per CTA in shared memory, so the per-candidate epilogue is one 16-bit shared load, one IMAD and half a
+//    three-input min; warps reduce with redux.sync.min and one shared atomicMin per work item.
 #include "kernels.h"
 
 #include <stdio.h>
@@ -45,6 +47,7 @@ struct TmaSearchArgs {
   int box_bytes;       // bytes of the window box
   int blk_bytes;       // bytes of the block box
   int stage_bytes;
+  int rank_off;        // byte offset of the spiral-rank table (uint16, (n + SEG) rows of n) in dynamic shared memory
   short2* mv;
   size_t mv_plane;
   unsigned long long* counters;
@@ -119,7 +122,7 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
   __shared__ __align__(8) uint64_t s_empty[kStages];
   __shared__ StageMeta s_meta[kStages];
   __shared__ uint32_t s_sdone[kStages];
-  __shared__ unsigned long long s_bkey[kBlockSlots];
+  __shared__ uint32_t s_bkey[kBlockSlots];
   __shared__ uint32_t s_bdone[kBlockSlots];
   __shared__ uint32_t s_next;
 
@@ -137,12 +140,19 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
       s_sdone[i] = 0;
     }
     for (int i = 0; i < kBlockSlots; ++i) {
-      s_bkey[i] = ~0ull;
+      s_bkey[i] = 0xffffffffu;
       s_bdone[i] = 0;
     }
     s_next = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  // spiral visit rank of every displacement, row-major [dy + R][dx + R]; rows past n hold 0xffff
+  constexpr int KS = BS >= 32 ? 14 : 16;  // key = SAD << KS | rank; SAD < 2^(32-KS), rank < 2^KS (checked on the host)
+  uint16_t* s_rank = reinterpret_cast<uint16_t*>(smem + a.rank_off);
+  for (int i = threadIdx.x; i < (a.n + SEG) * a.n; i += blockDim.x) {
+    const int ry = i / a.n, rx = i - ry * a.n;
+    s_rank[i] = ry < a.n ? (uint16_t)spiral_rank(rx - a.R, ry - a.R) : (uint16_t)0xffffu;
   }
   __syncthreads();
 
@@ -246,28 +256,28 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
           }
         }
 
-        // lane-local argmin on (SAD, spiral rank); rank only computed when the SAD can still win
-        unsigned long long best = ~0ull;
+        // lane-local argmin on key = SAD << KS | rank.  Lanes whose SEG candidates are all in bounds (nearly all
+        // of them) take the branch-free path; the others mask candidate by candidate.
         const int dx = o - a.R;
         const int px = m.x2 + dx;
         const bool xok = active && px >= 0 && px + BS <= a.w;
-        const int dy0 = m.band * a.band_rows + cy0 - a.R;
+        const int dyf = m.band * a.band_rows + cy0 - a.R;       // dy of candidate c = 0
+        const int c_lo = max(0, -(m.y2 + dyf));                 // py >= 0
+        const int c_hi = min(min(SEG - 1, a.R - dyf), a.h - BS - m.y2 - dyf);  // dy <= R and py + BS <= h
+        const uint16_t* rk = s_rank + (size_t)(m.band * a.band_rows + cy0) * a.n + o;
+        uint32_t best = 0xffffffffu;
+        if (xok && c_lo == 0 && c_hi == SEG - 1) {
 #pragma unroll
-        for (int c = 0; c < SEG; ++c) {
-          const int dy = dy0 + c;
-          const int py = m.y2 + dy;
-          const bool ok = xok && dy <= a.R && py >= 0 && py + BS <= a.h;
-          if (ok && acc[c] <= (uint32_t)(best >> 32)) {
-            const unsigned long long key = ((unsigned long long)acc[c] << 32) | spiral_rank(dx, dy);
-            best = key < best ? key : best;
+          for (int c = 0; c < SEG; ++c) best = min(best, (acc[c] << KS) + (uint32_t)rk[c * a.n]);
+        } else if (xok) {
+#pragma unroll
+          for (int c = 0; c < SEG; ++c) {
+            const uint32_t key = (acc[c] << KS) + (uint32_t)rk[c * a.n];
+            best = (c >= c_lo && c <= c_hi) ? min(best, key) : best;
           }
         }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-          const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, off);
-          best = other < best ? other : best;
-        }
-        if (lane == 0 && best != ~0ull) atomicMin(&s_bkey[m.bslot], best);
+        best = __reduce_min_sync(0xffffffffu, best);
+        if (lane == 0 && best != 0xffffffffu) atomicMin(&s_bkey[m.bslot], best);
       }
     }
     __syncwarp();
@@ -280,14 +290,14 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
         const uint32_t bd = atomicAdd(&s_bdone[m.bslot], 1u);
         if (bd == (uint32_t)a.nbands - 1u) {
           __threadfence_block();
-          const unsigned long long key = *reinterpret_cast<volatile unsigned long long*>(&s_bkey[m.bslot]);
-          s_bkey[m.bslot] = ~0ull;
+          const uint32_t key = *reinterpret_cast<volatile uint32_t*>(&s_bkey[m.bslot]);
+          s_bkey[m.bslot] = 0xffffffffu;
           s_bdone[m.bslot] = 0;
           const int pair = m.gblk / nblocks, b = m.gblk - pair * nblocks;
           short2 out = make_short2(0, 0);
           if (m.valid) {
             int dx, dy;
-            spiral_unrank((uint32_t)key, dx, dy);
+            spiral_unrank(key & ((1u << KS) - 1u), dx, dy);
             out = make_short2((short)(m.predx + dx), (short)(m.predy + dy));
             if (a.counters) {
               const int nx = min(a.R, a.w - BS - m.x2) - max(-a.R, -m.x2) + 1;
@@ -369,6 +379,7 @@ static bool make_geom(int w, int h, int bs, int R, TmaGeom* g) {
   if (R < 1) return false;
   memset(g, 0, sizeof(*g));
   const int n = 2 * R + 1;
+  if (n * n > (bs >= 32 ? (1 << 14) : (1 << 16)) - 1) return false;  // spiral rank must fit the key's low bits
   const int seg = pick_seg(bs, R);
   // staged box: starts at the 16-byte aligned column at or below (x2 - R); a lane reads words
   // (off + o) >> 2 ... + bs/4 inclusive, with off <= 15 and o <= 2R
@@ -405,7 +416,8 @@ static bool make_geom(int w, int h, int bs, int R, TmaGeom* g) {
   g->a.pww = box_w / 4;
   g->a.box_bytes = g->box_h * box_w;
   g->a.blk_bytes = blk_bytes;
-  g->smem = (size_t)kStages * g->a.stage_bytes;
+  g->a.rank_off = kStages * g->a.stage_bytes;
+  g->smem = (size_t)g->a.rank_off + (((size_t)(n + seg) * n * 2 + 127) / 128) * 128;
   return true;
 }
 

@@ -69,7 +69,7 @@ typedef struct {
   uint32_t fix_blocks;     /* blocks re-evaluated in those rounds */
   uint32_t search_kernel_used; /* bbme_stage_search only: 1 = generic kernel ran, 2 = TMA kernel ran */
   uint32_t search_launches;    /* search-kernel launches behind ms_search */
-  uint32_t reserved;
+  uint32_t reserved;           /* fix_blocks that were re-evaluated in the per-pair tail loop (the rest ran grid-wide) */
   uint64_t search_candidates; /* in-bounds candidate positions evaluated (== oracle search_sad_calls) */
   uint64_t search_absdiffs;   /* pixels |a-b| in the search (== oracle search_absdiffs) */
 } bbme_stats;
@@ -110,6 +110,12 @@ int bbme_estimate(bbme_ctx* ctx, const uint8_t* im1, const uint8_t* im2, size_t 
  * Pairs are processed in chunks of chunk_pairs over `slots` streams. */
 int bbme_estimate_batch(bbme_ctx* ctx, int n, const uint8_t* const* im1, const uint8_t* const* im2,
                         size_t pitch_bytes, float* const* flow);
+
+/* Same as bbme_estimate_batch but returns after enqueueing the copies and kernels; the results are in `flow` after
+ * the next bbme_sync.  Successive calls pipeline over the slots (the D2H of one call overlaps the H2D and kernels of
+ * the next).  Host buffers must be pinned (bbme_host_alloc / cudaHostAlloc) and stay valid until bbme_sync. */
+int bbme_estimate_batch_async(bbme_ctx* ctx, int n, const uint8_t* const* im1, const uint8_t* const* im2,
+                              size_t pitch_bytes, float* const* flow);
 
 /* n <= chunk_pairs pairs already in device memory (same device as the context).  Frames are n planes of
  * `plane_stride` bytes; flow is n planes of flow_plane_stride floats.  Runs on slot 0's stream and returns
