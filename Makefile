@@ -16,7 +16,7 @@ $(CSRC)/flo.o: $(CSRC)/flo.cpp include/bbme.h
 	g++ -O2 -ffp-contract=off -fPIC -std=c++17 -Wall -Iinclude -c $< -o $@
 
 $(LIB): $(OBJS)
-	$(NVCC) -shared -o $@ $(OBJS) -cudart static
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -shared -o $@ $(OBJS) -cudart static
 
 oracle:
 	$(MAKE) -C oracle

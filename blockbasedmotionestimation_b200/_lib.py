@@ -59,6 +59,7 @@ SIGNATURES = {
     "bbme_estimate_batch_async": (_I, [_P, _I, C.POINTER(_P), C.POINTER(_P), _SZ, C.POINTER(_P)]),
     "bbme_estimate_device": (_I, [_P, _I, _P, _P, _SZ, _SZ, _P, _SZ]),
     "bbme_estimate_device_compact": (_I, [_P, _I, _P, _P, _SZ, _SZ, _P, _SZ]),
+    "bbme_estimate_device_both": (_I, [_P, _I, _P, _P, _SZ, _SZ, _P, _SZ, _P, _SZ]),
     "bbme_sync": (_I, [_P]),
     "bbme_get_stats": (_I, [_P, C.POINTER(BbmeStats)]),
     "bbme_set_streams": (_I, [_P, _I, C.POINTER(_P)]),

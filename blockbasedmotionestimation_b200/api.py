@@ -174,6 +174,12 @@ class Estimator:
                                                       int(plane), C.c_void_p(d_mv), int(mv_plane)),
                "bbme_estimate_device_compact")
 
+    def estimate_device_both(self, n, d_im1, d_im2, pitch, plane, d_flow, flow_plane, d_mv, mv_plane):
+        _check(self._lib, self._ctx,
+               self._lib.bbme_estimate_device_both(self._ctx, int(n), C.c_void_p(d_im1), C.c_void_p(d_im2), int(pitch),
+                                                   int(plane), C.c_void_p(d_flow), int(flow_plane), C.c_void_p(d_mv),
+                                                   int(mv_plane)), "bbme_estimate_device_both")
+
     def set_streams(self, handles):
         """Run slot i on the caller's CUDA stream handles[i] (e.g. torch.cuda.Stream().cuda_stream)."""
         arr = (C.c_void_p * len(handles))(*[C.c_void_p(int(h)) for h in handles])

@@ -65,7 +65,7 @@ struct bbme_ctx {
   uint32_t search_launches = 0;
   bool stats_armed = false;
   int next_slot = 0;    // round-robin position over the slots across asynchronous calls
-  int grid_rounds = 3;  // fix-up rounds run grid-wide before the per-pair tail loop (BBME_GRID_ROUNDS)
+  int grid_rounds = -1;  // fix-up rounds run grid-wide before the per-pair tail loop; -1 = by chunk size (BBME_GRID_ROUNDS)
 };
 
 namespace {
@@ -263,10 +263,12 @@ int run_chunk(bbme_ctx* c, Slot& s, int n, const uint8_t* d_in1, const uint8_t* 
         ra.stamp = s.stamp;
         ra.wl_plane = c->cap[0];
         ra.ctr = s.ctr;
+        // with few pairs in flight the per-pair tail loop leaves most SMs idle: run the first (largest) rounds grid-wide
+        const int gr = c->grid_rounds >= 0 ? c->grid_rounds : (n >= 96 ? 0 : 3);
         launch_reg_full(ra, n, st);
-        for (int r = 0; r < c->grid_rounds; ++r) launch_reg_round(ra, r, n, st);
-        launch_reg_fix(ra, c->grid_rounds, n, st);
-        c->launches += 2 + c->grid_rounds;
+        for (int r = 0; r < gr; ++r) launch_reg_round(ra, r, n, st);
+        launch_reg_fix(ra, gr, n, st);
+        c->launches += 2 + gr;
         short2* t = cur; cur = nxt; nxt = t;
       }
       if (g > 2) {
@@ -611,6 +613,12 @@ int bbme_estimate_device_compact(bbme_ctx* c, int n, const uint8_t* d1, const ui
   return estimate_device_impl(c, n, d1, d2, pitch, plane, nullptr, 0, d_mv, mv_plane);
 }
 
+int bbme_estimate_device_both(bbme_ctx* c, int n, const uint8_t* d1, const uint8_t* d2, size_t pitch, size_t plane,
+                              float* d_flow, size_t flow_plane, int16_t* d_mv, size_t mv_plane) {
+  if (!d_flow && !d_mv) return c ? fail(c, BBME_E_ARG, "bbme_estimate_device_both: no output buffer") : BBME_E_ARG;
+  return estimate_device_impl(c, n, d1, d2, pitch, plane, d_flow, flow_plane, d_mv, mv_plane);
+}
+
 int bbme_host_alloc(void** p, size_t bytes) {
   if (!p) return BBME_E_ARG;
   return cudaHostAlloc(p, bytes, cudaHostAllocDefault) == cudaSuccess ? BBME_OK : BBME_E_NOMEM;
@@ -785,9 +793,10 @@ int bbme_stage_regularize(bbme_ctx* c, const uint8_t* im1, const uint8_t* im2, i
   ra.lm = lambda * (float)mult;
   ra.O = O; ra.Y = Y; ra.mv_plane = nb;
   ra.list0 = l0; ra.list1 = l1; ra.nv = nv; ra.stamp = stamp; ra.wl_plane = nb; ra.ctr = ctr;
+  const int gr = c->grid_rounds >= 0 ? c->grid_rounds : 3;
   launch_reg_full(ra, 1, 0);
-  for (int r = 0; r < c->grid_rounds; ++r) launch_reg_round(ra, r, 1, 0);
-  launch_reg_fix(ra, c->grid_rounds, 1, 0);
+  for (int r = 0; r < gr; ++r) launch_reg_round(ra, r, 1, 0);
+  launch_reg_fix(ra, gr, 1, 0);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return fail(c, BBME_E_CUDA, "stage_regularize kernel failed: %s", cudaGetErrorString(e));
   CUDA_TRY(c, cudaMemcpy(mv, Y, nb * sizeof(short2), cudaMemcpyDeviceToHost));

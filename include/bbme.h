@@ -128,6 +128,11 @@ int bbme_estimate_device(bbme_ctx* ctx, int n, const uint8_t* d_im1, const uint8
 int bbme_estimate_device_compact(bbme_ctx* ctx, int n, const uint8_t* d_im1, const uint8_t* d_im2,
                                  size_t pitch_bytes, size_t plane_stride, int16_t* d_mv, size_t mv_plane_stride);
 
+/* Both outputs of one run: the dense field (may be NULL) and the compact field (may be NULL), at least one given. */
+int bbme_estimate_device_both(bbme_ctx* ctx, int n, const uint8_t* d_im1, const uint8_t* d_im2, size_t pitch_bytes,
+                              size_t plane_stride, float* d_flow, size_t flow_plane_stride, int16_t* d_mv,
+                              size_t mv_plane_stride);
+
 /* Waits for all slots; with collect_stats it then folds the CUDA-event intervals and work counters of everything
  * enqueued since the previous bbme_sync / bbme_estimate_batch into the stats. */
 int bbme_sync(bbme_ctx* ctx);

@@ -1,0 +1,3 @@
+// Drop-in for the reference header of the same name (class PyramidLevel): see include/bbme/dropin.hpp.
+#pragma once
+#include "bbme/dropin.hpp"

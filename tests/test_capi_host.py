@@ -1,0 +1,157 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every symbol include/bbme.h declares,
+the shape planner equals the oracle's, the .flo codec / AEE equal the golden answers, and without a GPU the library
+fails loudly instead of falling back.  No compute kernels are launched here."""
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import blockbasedmotionestimation_b200 as bb
+from blockbasedmotionestimation_b200 import _lib
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(HERE, "golden")
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "bbme.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(bbme_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 30
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH], text=True)
+    exported = set(re.findall(r" T (bbme_[a-z0-9_]+)", out))
+    assert set(declared) <= exported, sorted(set(declared) - exported)
+    assert set(declared) == set(_lib.SIGNATURES), sorted(set(declared) ^ set(_lib.SIGNATURES))
+    assert lib.bbme_version() == 100
+
+
+def test_library_contains_sm100a_code_only():
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump not available")
+    archs = set(re.findall(r"sm_(\d+a?)", out.stdout))
+    assert archs == {"100a"}, archs
+
+
+def test_plan_shape_equals_oracle(oracle):
+    rng = np.random.default_rng(3)
+    checked = 0
+    for _ in range(300):
+        w, h = int(rng.integers(4, 700)), int(rng.integers(4, 700))
+        L = int(rng.integers(1, 5))
+        bs = [int(2 ** rng.integers(1, 6)) for _ in range(L)]
+        ss = [b + 8 for b in bs]
+        rc_o, sh_o = oracle.plan_shape(w, h, bs)
+        try:
+            sh = bb.plan_shape(w, h, ss, bs)
+            rc = 0
+        except bb.BbmeError as e:
+            rc = e.status
+        assert rc == rc_o, (w, h, bs, rc, rc_o)
+        if rc == 0:
+            checked += 1
+            for k in ("padded_width", "padded_height", "padding_x", "padding_y", "level_width", "level_height"):
+                assert sh[k] == sh_o[k], (w, h, bs, k)
+    assert checked > 20
+
+
+def test_baseline_config_shapes():
+    sh = bb.plan_shape(2336, 1552, [64] * 4, [32] * 4)  # RubberWhale x4, repo defaults (main_class.cpp:19-21,32-33)
+    assert (sh["padded_width"], sh["padded_height"], sh["padding_x"], sh["padding_y"]) == (2560, 1792, 112, 120)
+    assert sh["level_width"] == [2560, 1280, 640, 320]
+    sh = bb.plan_shape(1920, 1080, [80] * 3, [16] * 3)
+    assert (sh["padded_width"], sh["padded_height"], sh["padding_y"]) == (1920, 1088, 4)
+
+
+def test_invalid_arguments_have_status_codes():
+    for args, status in [((100, 100, [12], [6]), -1), ((3, 64, [16], [8]), -2), ((101, 96, [16], [8]), -3),
+                         ((8, 96, [16], [8]), -4), ((20000, 64, [16], [8]), -10)]:
+        with pytest.raises(bb.BbmeError) as e:
+            bb.plan_shape(*args)
+        assert e.value.status == status, (args, e.value.status)
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(bb.BbmeError) as e:
+        bb.Estimator(64, 64, [16], [8])
+    assert "no CPU fallback" in str(e.value)
+    with pytest.raises(bb.BbmeError):
+        bb.MF(np.zeros((64, 64), np.uint8), np.zeros((64, 64), np.uint8), [16], [8], 1)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under the package or include/ may import, include, link or call it."""
+    pat = re.compile(r"(from|import)\s+oracle|oracle/|bbme_oracle|\borc_[a-z]|libbbme_ref|cvshim")
+    for top in (os.path.join(ROOT, "blockbasedmotionestimation_b200"), os.path.join(ROOT, "include")):
+        for dirpath, _, files in os.walk(top):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                    text = open(os.path.join(dirpath, f), errors="ignore").read()
+                    assert not pat.search(text), os.path.join(dirpath, f)
+    mk = open(os.path.join(ROOT, "Makefile")).read()
+    link_line = [l for l in mk.splitlines() if "-shared" in l and "$(OBJS)" in l]
+    assert link_line and "oracle" not in link_line[0]
+
+
+def test_flow_class_codec_and_metric(tmp_path):
+    digest = json.load(open(os.path.join(GOLD, "flo_gt_digest.json")))
+    fl = bb.Flow()
+    crop = fl.ReadFlowFile(os.path.join(GOLD, "rubberwhale_crop.flo"))
+    assert crop.shape == (64, 96, 2) and crop.dtype == np.float32
+    est = np.zeros_like(crop)
+    est[..., 0] = 0.25
+    assert fl.CalculateMSE(crop, est) == pytest.approx(digest["rubberwhale_crop"]["aee_of_quarter_pixel_field"], rel=0, abs=1e-12)
+    out = tmp_path / "w.flo"
+    fl.WriteFlowFile(crop, out)
+    assert open(out, "rb").read() == open(os.path.join(GOLD, "rubberwhale_crop.flo"), "rb").read()
+    raw = open(out, "rb").read()
+    for payload, name in ((raw[:-4], "short.flo"), (raw + b"\0", "long.flo"), (b"XXXX" + raw[4:], "tag.flo"), (raw, "ext.txt")):
+        p = tmp_path / name
+        p.write_bytes(payload)
+        with pytest.raises(bb.BbmeError):
+            fl.ReadFlowFile(p)
+    with pytest.raises(bb.BbmeError):
+        fl.WriteFlowFile(crop, tmp_path / "noext")
+    with pytest.raises(bb.BbmeError):
+        fl.ReadFlowFile(None)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not present (GPU box)")
+def test_flow_class_roundtrips_gt_files(tmp_path):
+    digest = json.load(open(os.path.join(GOLD, "flo_gt_digest.json")))
+    fl = bb.Flow()
+    for seq, d in digest.items():
+        if "sha256" not in d:
+            continue
+        path = f"/root/reference/middlebury/gt-flow/{seq}/flow10.flo"
+        gt = fl.ReadFlowFile(path)
+        assert gt.shape == (d["height"], d["width"], 2)
+        assert fl.CalculateMSE(gt, np.zeros_like(gt)) == pytest.approx(d["aee_of_zero_field"], rel=0, abs=1e-12)
+        out = tmp_path / (seq + ".flo")
+        fl.WriteFlowFile(gt, out)
+        assert open(out, "rb").read() == open(path, "rb").read()
+
+
+def test_strip_and_subsample_like_main():
+    # main_class.cpp:58-70 on a synthetic padded field
+    sh = bb.plan_shape(2336, 1552, [64] * 4, [32] * 4)
+    rng = np.random.default_rng(1)
+    flow = rng.integers(-40, 40, (sh["padded_height"], sh["padded_width"], 2)).astype(np.float32)
+    out = bb.Flow().StripAndSubsample(flow, sh, 4)
+    assert out.shape == (388, 584, 2)
+    px, py = sh["padding_x"], sh["padding_y"]
+    want = flow[py:sh["padded_height"] - py:4, px:sh["padded_width"] - px:4] / 4.0
+    assert np.array_equal(out, want)

@@ -1,0 +1,32 @@
+"""A C++ caller written against the reference's class API (MF / Flow), compiled against include/ and libbbme.so."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import blockbasedmotionestimation_b200 as bb
+from helpers import make_pair
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cpp_dropin_matches_oracle(tmp_path, oracle):
+    exe = tmp_path / "dropin_main"
+    libdir = os.path.join(ROOT, "blockbasedmotionestimation_b200")
+    subprocess.check_call(["g++", "-std=c++11", "-O2", "-I" + os.path.join(ROOT, "include"), "-o", str(exe),
+                           os.path.join(ROOT, "tests", "cpp", "dropin_main.cpp"), "-L" + libdir, "-lbbme",
+                           "-Wl,-rpath," + libdir])
+    h, w, ss, bs = 90, 122, [20, 20, 20], [8, 8, 8]
+    f1, f2 = make_pair(h, w, 31, shift=(2, -1))
+    f1.tofile(tmp_path / "f1.raw")
+    f2.tofile(tmp_path / "f2.raw")
+    out = tmp_path / "out.flo"
+    args = [str(exe), str(w), str(h), str(tmp_path / "f1.raw"), str(tmp_path / "f2.raw"), str(out), "3"] + [str(v) for v in ss + bs]
+    res = subprocess.run(args, capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "padded 128x96 pad (3,3)" in res.stdout
+    got = bb.Flow().ReadFlowFile(out)
+    want, _ = oracle.estimate(f1, f2, ss, bs, 2)
+    assert np.array_equal(got, want[3:3 + h, 3:3 + w])
