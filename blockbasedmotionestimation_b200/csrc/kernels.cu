@@ -525,25 +525,73 @@ __device__ __forceinline__ short2 reg_eval_any(const RegArgs& a, int pair, const
   }
 }
 
-// Pass 1 of a sweep: every block evaluated with the OLD field for all nine slots (a Jacobi step).  Blocks
-// whose value changed enqueue their dependents: those may have used a stale "pred" value.
-template <int TEAM>
-__global__ void __launch_bounds__(128, TEAM <= 2 ? 4 : 1) k_reg_full(RegArgs a) {
-  constexpr int TEAMSZ = TEAM <= 2 ? 1 : TEAM;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  int i = t / TEAMSZ;
-  const int tl = t % TEAMSZ;
+// Pass 1 of a sweep (a Jacobi step: every block evaluated with the OLD field in all nine slots), in two kernels:
+//  k_reg_classify  one thread per block, ~20 registers, full occupancy: blocks whose nine candidates are identical
+//                  keep their vector (all energies equal, index 0 wins, :653-659) and are done; the others are
+//                  compacted into the evaluation list (warp-aggregated append, so neighbours stay neighbours).
+//                  On real fields 80-96 % of the 2x2 / 4x4 blocks are of the first kind.
+//  k_reg_eval      dense evaluation of the listed blocks; blocks whose value changed enqueue their dependents
+//                  (they may have used a stale "pred" value) for the fix-up rounds.
+__global__ void __launch_bounds__(256) k_reg_classify(RegArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int pair = blockIdx.y;
-  const bool live = i < a.gw * a.gh;
+  const int gw = a.gw, gh = a.gh;
+  const bool live = i < gw * gh;
+  const short2* __restrict__ O = a.O + (size_t)pair * a.mv_plane;
+  bool work = false;
+  if (live) {
+    const int bx = i % gw, by = i / gw;
+    const bool up = by > 0, dn = by < gh - 1, lf = bx > 0, rt = bx < gw - 1;
+    const short2 c0 = O[i];
+    const uint32_t k0 = pack_mv(c0);
+    bool same = true;
+    if (lf) same = same && pack_mv(O[i - 1]) == k0;
+    if (rt) same = same && pack_mv(O[i + 1]) == k0;
+    if (up) {
+      same = same && pack_mv(O[i - gw]) == k0;
+      if (lf) same = same && pack_mv(O[i - gw - 1]) == k0;
+      if (rt) same = same && pack_mv(O[i - gw + 1]) == k0;
+    }
+    if (dn) {
+      same = same && pack_mv(O[i + gw]) == k0;
+      if (lf) same = same && pack_mv(O[i + gw - 1]) == k0;
+      if (rt) same = same && pack_mv(O[i + gw + 1]) == k0;
+    }
+    if (same) a.Y[(size_t)pair * a.mv_plane + i] = c0;
+    work = !same;
+  }
+  const uint32_t m = __ballot_sync(0xffffffffu, work);
+  if (m) {
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(&a.ctr[(size_t)pair * kCtrWords + CTR_COUNT_EVAL], (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (work) a.list1[(size_t)pair * a.wl_plane + base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
+  }
+}
+
+template <int TEAM>
+__global__ void __launch_bounds__(128, TEAM <= 2 ? 4 : 1) k_reg_eval(RegArgs a) {
+  constexpr int TEAMSZ = TEAM <= 2 ? 1 : TEAM;
+  const int pair = blockIdx.y;
+  uint32_t* ctr = a.ctr + (size_t)pair * kCtrWords;
+  const uint32_t cnt = ctr[CTR_COUNT_EVAL];
+  const uint32_t first = (uint32_t)(blockIdx.x * blockDim.x) / TEAMSZ;
+  if (first >= cnt) return;  // the grid is sized for "every block listed"
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t e = t / TEAMSZ;
+  const int tl = (int)(t % TEAMSZ);
+  const bool live = e < cnt;
   if (!live) {
-    if (TEAMSZ > 1) return;  // whole teams leave together (blockDim is a multiple of TEAM)
-    i = a.gw * a.gh - 1;     // one thread per block: keep the warp converged for the warp-uniform early-out
+    if (TEAMSZ > 1) return;  // whole teams leave together
+    e = cnt - 1;             // one thread per block: keep the warp converged
   }
   const uint32_t team_mask = TEAMSZ >= 32 ? 0xffffffffu : (((1u << TEAMSZ) - 1u) << ((threadIdx.x & 31) / TEAMSZ * TEAMSZ));
-  const int bx = i % a.gw, by = i / a.gw;
   const short2* O = a.O + (size_t)pair * a.mv_plane;
   short2* Y = a.Y + (size_t)pair * a.mv_plane;
-  uint32_t* ctr = a.ctr + (size_t)pair * kCtrWords;
+  const int i = (int)a.list1[(size_t)pair * a.wl_plane + e];
+  const int bx = i % a.gw, by = i / a.gw;
   const short2 nv = reg_eval_any<TEAM>(a, pair, O, O, bx, by, tl, team_mask, live);
   if (tl != 0 || !live) return;
   Y[i] = nv;
@@ -655,6 +703,7 @@ __global__ void __launch_bounds__(TEAM <= 2 ? 512 : 1024) k_reg_fix(RegArgs a, i
     ctr[CTR_COUNT0] = 0;
     ctr[CTR_COUNT1] = 0;
     ctr[CTR_COUNT2] = 0;
+    ctr[CTR_COUNT_EVAL] = 0;
     ctr[CTR_EPOCH] = ep;
     ctr[CTR_ROUNDS] += rounds;
     ctr[CTR_BLOCKS] += blocks;
@@ -668,13 +717,15 @@ static int team_for(int bs) { return bs >= 32 ? 32 : (bs >= 8 ? bs : (bs == 4 ? 
 void launch_reg_full(const RegArgs& a, int n, cudaStream_t s) {
   const int team = team_for(a.bs);
   const int lanes = team <= 2 ? 1 : team;
-  dim3 grid((unsigned)(((size_t)a.gw * a.gh * lanes + 127) / 128), n);
+  const size_t nb = (size_t)a.gw * a.gh;
+  k_reg_classify<<<dim3((unsigned)((nb + 255) / 256), n), 256, 0, s>>>(a);
+  dim3 grid((unsigned)((nb * lanes + 127) / 128), n);
   switch (team) {
-    case 32: k_reg_full<32><<<grid, 128, 0, s>>>(a); break;
-    case 16: k_reg_full<16><<<grid, 128, 0, s>>>(a); break;
-    case 8: k_reg_full<8><<<grid, 128, 0, s>>>(a); break;
-    case 2: k_reg_full<2><<<grid, 128, 0, s>>>(a); break;
-    default: k_reg_full<1><<<grid, 128, 0, s>>>(a); break;
+    case 32: k_reg_eval<32><<<grid, 128, 0, s>>>(a); break;
+    case 16: k_reg_eval<16><<<grid, 128, 0, s>>>(a); break;
+    case 8: k_reg_eval<8><<<grid, 128, 0, s>>>(a); break;
+    case 2: k_reg_eval<2><<<grid, 128, 0, s>>>(a); break;
+    default: k_reg_eval<1><<<grid, 128, 0, s>>>(a); break;
   }
 }
 

@@ -10,7 +10,7 @@ namespace bbme {
 
 // per-pair control words of the regularisation fix-up (device memory, kCtrWords uint32 per pair)
 constexpr int kCtrWords = 8;
-enum { CTR_COUNT0 = 0, CTR_COUNT1 = 1, CTR_EPOCH = 2, CTR_ROUNDS = 3, CTR_BLOCKS = 4, CTR_COUNT2 = 5, CTR_TAIL_BLOCKS = 6 };
+enum { CTR_COUNT0 = 0, CTR_COUNT1 = 1, CTR_EPOCH = 2, CTR_ROUNDS = 3, CTR_BLOCKS = 4, CTR_COUNT2 = 5, CTR_TAIL_BLOCKS = 6, CTR_COUNT_EVAL = 7 };
 
 struct RegArgs {
   ImgView i1, i2;
