@@ -108,7 +108,7 @@ __device__ __forceinline__ void spiral_unrank(uint32_t rank, int& dx, int& dy) {
   else { dy = -r; dx = (o - 6 * r) - r + 1; }
 }
 
-template <int BS, int SEG>
+template <int BS, int SEG, int PWW>
 __global__ void __launch_bounds__(kThreads, 2)
 k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant__ CUtensorMap map_blk,
              const TmaSearchArgs a) {
@@ -214,7 +214,7 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
         const int wi = bo >> 2;
         const int cy0 = sidx * SEG;
         const uint8_t* st = smem + (size_t)stage * a.stage_bytes;
-        const uint32_t* win = reinterpret_cast<const uint32_t*>(st) + (size_t)cy0 * a.pww + wi;
+        const uint32_t* win = reinterpret_cast<const uint32_t*>(st) + cy0 * PWW + wi;
         const uint8_t* blk = st + a.win_bytes + (BS == 8 ? ((m.x2 - m.predx) & 8) : 0);
 
         uint32_t acc[SEG];
@@ -236,13 +236,12 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
               A[y][0] = v.x; A[y][1 % TWW] = v.y;
             }
           }
-          const uint32_t* wb = win + (size_t)(qy * TW) * a.pww + qx * TWW;
+          const uint32_t* wb = win + qy * TW * PWW + qx * TWW;
 #pragma unroll
           for (int jr = 0; jr < SEG + TW - 1; ++jr) {
             uint32_t raw[TWW + 1], wv[TWW];
 #pragma unroll
-            for (int kk = 0; kk <= TWW; ++kk) raw[kk] = wb[kk];
-            wb += a.pww;
+            for (int kk = 0; kk <= TWW; ++kk) raw[kk] = wb[jr * PWW + kk];  // compile-time offsets: no address arithmetic
 #pragma unroll
             for (int kk = 0; kk < TWW; ++kk) wv[kk] = __funnelshift_r(raw[kk], raw[kk + 1], sh);
 #pragma unroll
@@ -350,10 +349,10 @@ static int encode_u8_3d(CUtensorMap* map, const uint8_t* base, int w, int h, int
 static int pick_seg(int bs, int R) {
   // lane efficiency of the flattened (column, segment) item space; candidates: instantiated SEG values
   const int n = 2 * R + 1;
-  const int cands[3] = {13, 11, 8};
+  const int cands[2] = {13, 11};
   int best = 13;
   double best_eff = -1.0;
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < 2; ++i) {
     const int seg = cands[i];
     const int segs = (n + seg - 1) / seg;
     const int items = n * segs;
@@ -384,8 +383,13 @@ static bool make_geom(int w, int h, int bs, int R, TmaGeom* g) {
   // staged box: starts at the 16-byte aligned column at or below (x2 - R); a lane reads words
   // (off + o) >> 2 ... + bs/4 inclusive, with off <= 15 and o <= 2R
   const int words = ((15 + 2 * R) >> 2) + bs / 4 + 1;
-  const int box_w = ((words * 4 + 15) / 16) * 16;
-  if (box_w > 256) return false;
+  // the row pitch is a template parameter of the kernel: round up to the next instantiated class
+  static const int kPitchClasses[6] = {16, 24, 32, 40, 48, 64};
+  int pww = 0;
+  for (int i = 0; i < 6 && !pww; ++i)
+    if (words <= kPitchClasses[i]) pww = kPitchClasses[i];
+  if (!pww) return false;
+  const int box_w = pww * 4;
   const int segs_total = (n + seg - 1) / seg;
   const int blk_bytes = bs * (bs >= 16 ? bs : 16);
   const size_t budget = 24 * 1024;  // per stage
@@ -421,10 +425,10 @@ static bool make_geom(int w, int h, int bs, int R, TmaGeom* g) {
   return true;
 }
 
-template <int BS, int SEG>
+template <int BS, int SEG, int PWW>
 static void launch_inst(const TmaSearchPlan& plan, const TmaSearchArgs& a, int grid, cudaStream_t s) {
-  cudaFuncSetAttribute(k_search_tma<BS, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  k_search_tma<BS, SEG><<<grid, kThreads, plan.smem_bytes, s>>>(plan.map_win, plan.map_blk, a);
+  cudaFuncSetAttribute(k_search_tma<BS, SEG, PWW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  k_search_tma<BS, SEG, PWW><<<grid, kThreads, plan.smem_bytes, s>>>(plan.map_win, plan.map_blk, a);
 }
 
 int tma_search_plan(TmaSearchPlan* plan, const uint8_t* img1, const uint8_t* img2, int w, int h, int pitch,
@@ -468,11 +472,13 @@ void launch_search_tma(const TmaSearchPlan& plan, ImgView i1, ImgView i2, MvView
   const int total = a.gw * a.gh * n;
   int grid = sm_count * 2;
   if (grid > total) grid = total;
-#define BBME_CASE(BS_, SEG_) \
-  if (plan.bs == BS_ && plan.seg == SEG_) { launch_inst<BS_, SEG_>(plan, a, grid, s); return; }
-  BBME_CASE(8, 13) BBME_CASE(8, 11) BBME_CASE(8, 8)
-  BBME_CASE(16, 13) BBME_CASE(16, 11) BBME_CASE(16, 8)
-  BBME_CASE(32, 13) BBME_CASE(32, 11) BBME_CASE(32, 8)
+#define BBME_CASE(BS_, SEG_, PWW_) \
+  if (plan.bs == BS_ && plan.seg == SEG_ && a.pww == PWW_) { launch_inst<BS_, SEG_, PWW_>(plan, a, grid, s); return; }
+#define BBME_CASES(BS_, SEG_) \
+  BBME_CASE(BS_, SEG_, 16) BBME_CASE(BS_, SEG_, 24) BBME_CASE(BS_, SEG_, 32) BBME_CASE(BS_, SEG_, 40) \
+  BBME_CASE(BS_, SEG_, 48) BBME_CASE(BS_, SEG_, 64)
+  BBME_CASES(8, 13) BBME_CASES(8, 11) BBME_CASES(16, 13) BBME_CASES(16, 11) BBME_CASES(32, 13) BBME_CASES(32, 11)
+#undef BBME_CASES
 #undef BBME_CASE
 }
 
