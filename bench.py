@@ -395,7 +395,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=128)
     ap.add_argument("--slots", type=int, default=1)
     ap.add_argument("--e2e-chunk", type=int, default=32)
-    ap.add_argument("--e2e-slots", type=int, default=3)
+    ap.add_argument("--e2e-slots", type=int, default=4)
     ap.add_argument("--e2e-steps", type=int, default=1000, help="cap on the e2e arm's steps (default: same as --steps)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer arm")

@@ -190,127 +190,150 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
   }
 
   // -------------------------------------------------------------------- consumers
+  // One flat lane space per CTA: unit k owns lanes [k * IU, (k + 1) * IU), IU = n * segs_per_band (one lane = one
+  // displacement column x SEG rows).  A 32-lane work item is any aligned run of 32 lanes, so it may straddle two
+  // consecutive units (IU >= 32): no lane idles at unit boundaries.  Completion is counted in lanes.
+  const int IU = max(a.n * a.segs_per_band, 32);  // tiny search ranges: pad the unit to one full item (lanes past n * segs idle)
+  const int total_lanes = my_units * IU;
+  auto finish_unit = [&](int stage) {  // lane 0 of the warp that completed the unit's last lane
+    const StageMeta m = s_meta[stage];
+    s_sdone[stage] = 0;
+    const uint32_t bd = atomicAdd(&s_bdone[m.bslot], 1u);
+    if (bd == (uint32_t)a.nbands - 1u) {  // last band of the block
+      __threadfence_block();
+      const uint32_t key = *reinterpret_cast<volatile uint32_t*>(&s_bkey[m.bslot]);
+      s_bkey[m.bslot] = 0xffffffffu;
+      s_bdone[m.bslot] = 0;
+      const int pair = m.gblk / nblocks, b = m.gblk - pair * nblocks;
+      short2 out = make_short2(0, 0);
+      if (m.valid) {
+        int dx, dy;
+        spiral_unrank(key & ((1u << KS) - 1u), dx, dy);
+        out = make_short2((short)(m.predx + dx), (short)(m.predy + dy));
+        if (a.counters) {
+          const int nx = min(a.R, a.w - BS - m.x2) - max(-a.R, -m.x2) + 1;
+          const int ny = min(a.R, a.h - BS - m.y2) - max(-a.R, -m.y2) + 1;
+          atomicAdd(&a.counters[0], (unsigned long long)(nx * ny));
+          atomicAdd(&a.counters[1], (unsigned long long)(nx * ny) * (unsigned long long)(BS * BS));
+        }
+      }
+      a.mv[(size_t)pair * a.mv_plane + b] = out;
+    }
+    __threadfence_block();
+    mbar_arrive(&s_empty[stage]);
+  };
+
   for (;;) {
     uint32_t t = 0;
     if (lane == 0) t = atomicAdd(&s_next, 1u);
     t = __shfl_sync(0xffffffffu, t, 0);
-    const int k = (int)(t / (uint32_t)a.wi_max);
-    const int j = (int)t - k * a.wi_max;
-    if (k >= my_units) break;
-    const int stage = k % kStages;
-    mbar_wait(&s_full[stage], (uint32_t)(k / kStages) & 1u);
+    const int T0 = (int)t * 32;
+    if (T0 >= total_lanes) break;
+    const int k0 = T0 / IU;                              // unit of lane 0
+    const int split = (k0 + 1) * IU - T0;                // lanes [0, split) belong to k0, the rest to k0 + 1
+    const int k1 = (split < 32 && k0 + 1 < my_units) ? k0 + 1 : k0;
+    mbar_wait(&s_full[k0 % kStages], (uint32_t)(k0 / kStages) & 1u);
+    if (k1 != k0) mbar_wait(&s_full[k1 % kStages], (uint32_t)(k1 / kStages) & 1u);
+
+    const int T = T0 + lane;
+    const bool second = lane >= split;
+    const int kl = second ? k1 : k0;
+    const int stage = kl % kStages;
     const StageMeta m = s_meta[stage];
+    const int q = T - kl * IU;
+    const int segs_here = min(a.segs_per_band, a.segs_total - m.band * a.segs_per_band);
+    const int sidx_raw = q / a.n;
+    const bool active = T < total_lanes && (!second || k1 != k0) && m.valid && sidx_raw < segs_here;
+    const int qq = active ? q : 0;
+    const int sidx = qq / a.n, o = qq - sidx * a.n;
+    uint32_t best = 0xffffffffu;
 
-    if (m.valid) {
-      const int segs_here = min(a.segs_per_band, a.segs_total - m.band * a.segs_per_band);
-      const int items = a.n * segs_here;
-      const int q = j * 32 + lane;
-      if (j * 32 < items) {
-        const bool active = q < items;
-        const int qq = active ? q : 0;
-        const int sidx = qq / a.n, o = qq - sidx * a.n;
-        const int bo = m.off + o;                 // byte column of this lane's displacement inside the staged box
-        const uint32_t sh = (uint32_t)(bo & 3) * 8u;
-        const int wi = bo >> 2;
-        const int cy0 = sidx * SEG;
-        const uint8_t* st = smem + (size_t)stage * a.stage_bytes;
-        const uint32_t* win = reinterpret_cast<const uint32_t*>(st) + cy0 * PWW + wi;
-        const uint8_t* blk = st + a.win_bytes + (BS == 8 ? ((m.x2 - m.predx) & 8) : 0);
+    if (__any_sync(0xffffffffu, active)) {
+      const int bo = m.off + o;                 // byte column of this lane's displacement inside the staged box
+      const uint32_t sh = (uint32_t)(bo & 3) * 8u;
+      const int wi = bo >> 2;
+      const int cy0 = sidx * SEG;
+      const uint8_t* st = smem + (size_t)stage * a.stage_bytes;
+      const uint32_t* win = reinterpret_cast<const uint32_t*>(st) + cy0 * PWW + wi;
+      const uint8_t* blk = st + a.win_bytes + (BS == 8 ? ((m.x2 - m.predx) & 8) : 0);
 
-        uint32_t acc[SEG];
+      uint32_t acc[SEG];
 #pragma unroll
-        for (int c = 0; c < SEG; ++c) acc[c] = 0u;
+      for (int c = 0; c < SEG; ++c) acc[c] = 0u;
 
 #pragma unroll 1
-        for (int qi = 0; qi < QN * QN; ++qi) {
-          const int qy = qi / QN, qx = qi - qy * QN;
-          uint32_t A[TW][TWW];
+      for (int qi = 0; qi < QN * QN; ++qi) {
+        const int qy = qi / QN, qx = qi - qy * QN;
+        uint32_t A[TW][TWW];
 #pragma unroll
-          for (int y = 0; y < TW; ++y) {
-            const uint8_t* ar = blk + (size_t)(qy * TW + y) * AP + qx * TW;
-            if (TWW == 4) {
-              const uint4 v = *reinterpret_cast<const uint4*>(ar);
-              A[y][0] = v.x; A[y][1] = v.y; A[y][2 % TWW] = v.z; A[y][3 % TWW] = v.w;
-            } else {
-              const uint2 v = *reinterpret_cast<const uint2*>(ar);
-              A[y][0] = v.x; A[y][1 % TWW] = v.y;
-            }
+        for (int y = 0; y < TW; ++y) {
+          const uint8_t* ar = blk + (size_t)(qy * TW + y) * AP + qx * TW;
+          if (TWW == 4) {
+            const uint4 v = *reinterpret_cast<const uint4*>(ar);
+            A[y][0] = v.x; A[y][1] = v.y; A[y][2 % TWW] = v.z; A[y][3 % TWW] = v.w;
+          } else {
+            const uint2 v = *reinterpret_cast<const uint2*>(ar);
+            A[y][0] = v.x; A[y][1 % TWW] = v.y;
           }
-          const uint32_t* wb = win + qy * TW * PWW + qx * TWW;
+        }
+        const uint32_t* wb = win + qy * TW * PWW + qx * TWW;
 #pragma unroll
-          for (int jr = 0; jr < SEG + TW - 1; ++jr) {
-            uint32_t raw[TWW + 1], wv[TWW];
+        for (int jr = 0; jr < SEG + TW - 1; ++jr) {
+          uint32_t raw[TWW + 1], wv[TWW];
 #pragma unroll
-            for (int kk = 0; kk <= TWW; ++kk) raw[kk] = wb[jr * PWW + kk];  // compile-time offsets: no address arithmetic
+          for (int kk = 0; kk <= TWW; ++kk) raw[kk] = wb[jr * PWW + kk];  // compile-time offsets: no address arithmetic
 #pragma unroll
-            for (int kk = 0; kk < TWW; ++kk) wv[kk] = __funnelshift_r(raw[kk], raw[kk + 1], sh);
+          for (int kk = 0; kk < TWW; ++kk) wv[kk] = __funnelshift_r(raw[kk], raw[kk + 1], sh);
 #pragma unroll
-            for (int kk = 0; kk < TWW; ++kk) {
+          for (int kk = 0; kk < TWW; ++kk) {
 #pragma unroll
-              for (int y = 0; y < TW; ++y) {
-                const int c = jr - y;
-                if (c >= 0 && c < SEG) acc[c] = sad4(A[y][kk], wv[kk], acc[c]);
-              }
+            for (int y = 0; y < TW; ++y) {
+              const int c = jr - y;
+              if (c >= 0 && c < SEG) acc[c] = sad4(A[y][kk], wv[kk], acc[c]);
             }
           }
         }
+      }
 
-        // lane-local argmin on key = SAD << KS | rank.  Lanes whose SEG candidates are all in bounds (nearly all
-        // of them) take the branch-free path; the others mask candidate by candidate.
-        const int dx = o - a.R;
-        const int px = m.x2 + dx;
-        const bool xok = active && px >= 0 && px + BS <= a.w;
-        const int dyf = m.band * a.band_rows + cy0 - a.R;       // dy of candidate c = 0
-        const int c_lo = max(0, -(m.y2 + dyf));                 // py >= 0
-        const int c_hi = min(min(SEG - 1, a.R - dyf), a.h - BS - m.y2 - dyf);  // dy <= R and py + BS <= h
-        const uint16_t* rk = s_rank + (size_t)(m.band * a.band_rows + cy0) * a.n + o;
-        uint32_t best = 0xffffffffu;
-        if (xok && c_lo == 0 && c_hi == SEG - 1) {
+      // lane-local argmin on key = SAD << KS | rank.  Lanes whose SEG candidates are all in bounds (nearly all
+      // of them) take the branch-free path; the others mask candidate by candidate.
+      const int dx = o - a.R;
+      const int px = m.x2 + dx;
+      const bool xok = active && px >= 0 && px + BS <= a.w;
+      const int dyf = m.band * a.band_rows + cy0 - a.R;       // dy of candidate c = 0
+      const int c_lo = max(0, -(m.y2 + dyf));                 // py >= 0
+      const int c_hi = min(min(SEG - 1, a.R - dyf), a.h - BS - m.y2 - dyf);  // dy <= R and py + BS <= h
+      const uint16_t* rk = s_rank + (size_t)(m.band * a.band_rows + cy0) * a.n + o;
+      if (xok && c_lo == 0 && c_hi == SEG - 1) {
 #pragma unroll
-          for (int c = 0; c < SEG; ++c) best = min(best, (acc[c] << KS) + (uint32_t)rk[c * a.n]);
-        } else if (xok) {
+        for (int c = 0; c < SEG; ++c) best = min(best, (acc[c] << KS) + (uint32_t)rk[c * a.n]);
+      } else if (xok) {
 #pragma unroll
-          for (int c = 0; c < SEG; ++c) {
-            const uint32_t key = (acc[c] << KS) + (uint32_t)rk[c * a.n];
-            best = (c >= c_lo && c <= c_hi) ? min(best, key) : best;
-          }
+        for (int c = 0; c < SEG; ++c) {
+          const uint32_t key = (acc[c] << KS) + (uint32_t)rk[c * a.n];
+          best = (c >= c_lo && c <= c_hi) ? min(best, key) : best;
         }
-        best = __reduce_min_sync(0xffffffffu, best);
-        if (lane == 0 && best != 0xffffffffu) atomicMin(&s_bkey[m.bslot], best);
+      }
+    }
+    // per-unit reduction: lanes of k0, then lanes of k1
+    const uint32_t b0 = __reduce_min_sync(0xffffffffu, second ? 0xffffffffu : best);
+    const uint32_t b1 = __reduce_min_sync(0xffffffffu, second ? best : 0xffffffffu);
+    const int bslot0 = __shfl_sync(0xffffffffu, m.bslot, 0);
+    const int bslot1 = __shfl_sync(0xffffffffu, m.bslot, 31);
+    if (lane == 0) {
+      if (b0 != 0xffffffffu) atomicMin(&s_bkey[bslot0], b0);
+      if (k1 != k0 && b1 != 0xffffffffu) atomicMin(&s_bkey[bslot1], b1);
+      __threadfence_block();
+      const int n0 = min(32, split);
+      const uint32_t d0 = atomicAdd(&s_sdone[k0 % kStages], (uint32_t)n0);
+      if (d0 + (uint32_t)n0 == (uint32_t)IU) finish_unit(k0 % kStages);
+      if (k1 != k0) {
+        const int n1 = 32 - n0;
+        const uint32_t d1 = atomicAdd(&s_sdone[k1 % kStages], (uint32_t)n1);
+        if (d1 + (uint32_t)n1 == (uint32_t)IU) finish_unit(k1 % kStages);
       }
     }
     __syncwarp();
-    if (lane == 0) {
-      __threadfence_block();
-      const uint32_t d = atomicAdd(&s_sdone[stage], 1u);
-      if (d == (uint32_t)a.wi_max - 1u) {
-        // last work item of this unit: maybe last unit of the block
-        s_sdone[stage] = 0;
-        const uint32_t bd = atomicAdd(&s_bdone[m.bslot], 1u);
-        if (bd == (uint32_t)a.nbands - 1u) {
-          __threadfence_block();
-          const uint32_t key = *reinterpret_cast<volatile uint32_t*>(&s_bkey[m.bslot]);
-          s_bkey[m.bslot] = 0xffffffffu;
-          s_bdone[m.bslot] = 0;
-          const int pair = m.gblk / nblocks, b = m.gblk - pair * nblocks;
-          short2 out = make_short2(0, 0);
-          if (m.valid) {
-            int dx, dy;
-            spiral_unrank(key & ((1u << KS) - 1u), dx, dy);
-            out = make_short2((short)(m.predx + dx), (short)(m.predy + dy));
-            if (a.counters) {
-              const int nx = min(a.R, a.w - BS - m.x2) - max(-a.R, -m.x2) + 1;
-              const int ny = min(a.R, a.h - BS - m.y2) - max(-a.R, -m.y2) + 1;
-              atomicAdd(&a.counters[0], (unsigned long long)(nx * ny));
-              atomicAdd(&a.counters[1], (unsigned long long)(nx * ny) * (unsigned long long)(BS * BS));
-            }
-          }
-          a.mv[(size_t)pair * a.mv_plane + b] = out;
-        }
-        __threadfence_block();
-        mbar_arrive(&s_empty[stage]);
-      }
-    }
   }
 }
 
