@@ -20,6 +20,9 @@
 //  * Block results are reduced with a 32-bit key (SAD << KS | spiral rank); the ranks come from a table built once
 //    per CTA in shared memory, so the per-candidate epilogue is one 16-bit shared load, one IMAD and half a
 //    three-input min; warps reduce with redux.sync.min and one shared atomicMin per work item.
+//  * Large search ranges (K64 instantiations): when (2R+1)^2 does not fit the 32-bit key, the key is 64 bit
+//    (SAD << 32 | rank) and ranks are computed arithmetically; when the window is wider than one 256-byte TMA box it
+//    is staged as two boxes that overlap by 16 bytes and every lane picks the box that holds its five words.
 #include "kernels.h"
 
 #include <stdio.h>
@@ -48,6 +51,8 @@ struct TmaSearchArgs {
   int blk_bytes;       // bytes of the block box
   int stage_bytes;
   int rank_off;        // byte offset of the spiral-rank table (uint16, (n + SEG) rows of n) in dynamic shared memory
+  int box1_word;       // 0: one window box; else the word column where the second (overlapping) box starts
+  int box1_off_words;  // word offset of the second box inside a stage
   short2* mv;
   size_t mv_plane;
   unsigned long long* counters;
@@ -108,7 +113,7 @@ __device__ __forceinline__ void spiral_unrank(uint32_t rank, int& dx, int& dy) {
   else { dy = -r; dx = (o - 6 * r) - r + 1; }
 }
 
-template <int BS, int SEG, int PWW>
+template <int BS, int SEG, int PWW, bool K64>
 __global__ void __launch_bounds__(kThreads, 2)
 k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant__ CUtensorMap map_blk,
              const TmaSearchArgs a) {
@@ -123,6 +128,7 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
   __shared__ StageMeta s_meta[kStages];
   __shared__ uint32_t s_sdone[kStages];
   __shared__ uint32_t s_bkey[kBlockSlots];
+  __shared__ unsigned long long s_bkey64[kBlockSlots];
   __shared__ uint32_t s_bdone[kBlockSlots];
   __shared__ uint32_t s_next;
 
@@ -141,6 +147,7 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
     }
     for (int i = 0; i < kBlockSlots; ++i) {
       s_bkey[i] = 0xffffffffu;
+      s_bkey64[i] = ~0ull;
       s_bdone[i] = 0;
     }
     s_next = 0;
@@ -150,9 +157,11 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
   // spiral visit rank of every displacement, row-major [dy + R][dx + R]; rows past n hold 0xffff
   constexpr int KS = BS >= 32 ? 14 : 16;  // key = SAD << KS | rank; SAD < 2^(32-KS), rank < 2^KS (checked on the host)
   uint16_t* s_rank = reinterpret_cast<uint16_t*>(smem + a.rank_off);
-  for (int i = threadIdx.x; i < (a.n + SEG) * a.n; i += blockDim.x) {
-    const int ry = i / a.n, rx = i - ry * a.n;
-    s_rank[i] = ry < a.n ? (uint16_t)spiral_rank(rx - a.R, ry - a.R) : (uint16_t)0xffffu;
+  if (!K64) {
+    for (int i = threadIdx.x; i < (a.n + SEG) * a.n; i += blockDim.x) {
+      const int ry = i / a.n, rx = i - ry * a.n;
+      s_rank[i] = ry < a.n ? (uint16_t)spiral_rank(rx - a.R, ry - a.R) : (uint16_t)0xffffu;
+    }
   }
   __syncthreads();
 
@@ -177,9 +186,10 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
         s_meta[stage] = m;
         if (valid) {
           uint8_t* st = smem + (size_t)stage * a.stage_bytes;
-          mbar_arrive_expect_tx(&s_full[stage], (uint32_t)(a.box_bytes + a.blk_bytes));
+          mbar_arrive_expect_tx(&s_full[stage], (uint32_t)((a.box1_word ? 2 : 1) * a.box_bytes + a.blk_bytes));
           const int wy = y2 - a.R + band * a.band_rows;
           tma_load_3d(st, &map_win, &s_full[stage], wx_al, wy, pair);
+          if (a.box1_word) tma_load_3d(st + (size_t)a.box1_off_words * 4, &map_win, &s_full[stage], wx_al + 4 * a.box1_word, wy, pair);
           tma_load_3d(st + a.win_bytes, &map_blk, &s_full[stage], (bx * BS) & ~15, by * BS, pair);
         } else {
           mbar_arrive(&s_full[stage]);
@@ -201,14 +211,20 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
     const uint32_t bd = atomicAdd(&s_bdone[m.bslot], 1u);
     if (bd == (uint32_t)a.nbands - 1u) {  // last band of the block
       __threadfence_block();
-      const uint32_t key = *reinterpret_cast<volatile uint32_t*>(&s_bkey[m.bslot]);
-      s_bkey[m.bslot] = 0xffffffffu;
+      uint32_t key;  // the winner's spiral rank
+      if (K64) {
+        key = (uint32_t)*reinterpret_cast<volatile unsigned long long*>(&s_bkey64[m.bslot]);
+        s_bkey64[m.bslot] = ~0ull;
+      } else {
+        key = *reinterpret_cast<volatile uint32_t*>(&s_bkey[m.bslot]) & ((1u << KS) - 1u);
+        s_bkey[m.bslot] = 0xffffffffu;
+      }
       s_bdone[m.bslot] = 0;
       const int pair = m.gblk / nblocks, b = m.gblk - pair * nblocks;
       short2 out = make_short2(0, 0);
       if (m.valid) {
         int dx, dy;
-        spiral_unrank(key & ((1u << KS) - 1u), dx, dy);
+        spiral_unrank(key, dx, dy);
         out = make_short2((short)(m.predx + dx), (short)(m.predy + dy));
         if (a.counters) {
           const int nx = min(a.R, a.w - BS - m.x2) - max(-a.R, -m.x2) + 1;
@@ -246,7 +262,7 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
     const bool active = T < total_lanes && (!second || k1 != k0) && m.valid && sidx_raw < segs_here;
     const int qq = active ? q : 0;
     const int sidx = qq / a.n, o = qq - sidx * a.n;
-    uint32_t best = 0xffffffffu;
+    uint32_t best = 0xffffffffu, best_rank = 0xffffffffu;  // K64: best = SAD, best_rank = its spiral rank
 
     if (__any_sync(0xffffffffu, active)) {
       const int bo = m.off + o;                 // byte column of this lane's displacement inside the staged box
@@ -254,7 +270,7 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
       const int wi = bo >> 2;
       const int cy0 = sidx * SEG;
       const uint8_t* st = smem + (size_t)stage * a.stage_bytes;
-      const uint32_t* win = reinterpret_cast<const uint32_t*>(st) + cy0 * PWW + wi;
+      const uint32_t* win = reinterpret_cast<const uint32_t*>(st) + cy0 * PWW;
       const uint8_t* blk = st + a.win_bytes + (BS == 8 ? ((m.x2 - m.predx) & 8) : 0);
 
       uint32_t acc[SEG];
@@ -276,7 +292,9 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
             A[y][0] = v.x; A[y][1 % TWW] = v.y;
           }
         }
-        const uint32_t* wb = win + qy * TW * PWW + qx * TWW;
+        // word column of this lane's tile row start; with two boxes, take the one that holds words wq .. wq + TWW
+        const int wq = wi + qx * TWW;
+        const uint32_t* wb = win + qy * TW * PWW + ((a.box1_word && wq > PWW - 1 - TWW) ? a.box1_off_words + wq - a.box1_word : wq);
 #pragma unroll
         for (int jr = 0; jr < SEG + TW - 1; ++jr) {
           uint32_t raw[TWW + 1], wv[TWW];
@@ -303,26 +321,48 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
       const int dyf = m.band * a.band_rows + cy0 - a.R;       // dy of candidate c = 0
       const int c_lo = max(0, -(m.y2 + dyf));                 // py >= 0
       const int c_hi = min(min(SEG - 1, a.R - dyf), a.h - BS - m.y2 - dyf);  // dy <= R and py + BS <= h
-      const uint16_t* rk = s_rank + (size_t)(m.band * a.band_rows + cy0) * a.n + o;
-      if (xok && c_lo == 0 && c_hi == SEG - 1) {
-#pragma unroll
-        for (int c = 0; c < SEG; ++c) best = min(best, (acc[c] << KS) + (uint32_t)rk[c * a.n]);
-      } else if (xok) {
+      if (K64) {
+        // 64-bit key: (SAD, spiral rank), the rank computed from (dx, dy); kept as two words until the reduction
 #pragma unroll
         for (int c = 0; c < SEG; ++c) {
-          const uint32_t key = (acc[c] << KS) + (uint32_t)rk[c * a.n];
-          best = (c >= c_lo && c <= c_hi) ? min(best, key) : best;
+          const uint32_t rank = spiral_rank(dx, dyf + c);
+          const bool ok = xok && c >= c_lo && c <= c_hi;
+          const bool better = ok && (acc[c] < best || (acc[c] == best && rank < best_rank));
+          best = better ? acc[c] : best;
+          best_rank = better ? rank : best_rank;
+        }
+      } else {
+        const uint16_t* rk = s_rank + (size_t)(m.band * a.band_rows + cy0) * a.n + o;
+        if (xok && c_lo == 0 && c_hi == SEG - 1) {
+#pragma unroll
+          for (int c = 0; c < SEG; ++c) best = min(best, (acc[c] << KS) + (uint32_t)rk[c * a.n]);
+        } else if (xok) {
+#pragma unroll
+          for (int c = 0; c < SEG; ++c) {
+            const uint32_t key = (acc[c] << KS) + (uint32_t)rk[c * a.n];
+            best = (c >= c_lo && c <= c_hi) ? min(best, key) : best;
+          }
         }
       }
     }
     // per-unit reduction: lanes of k0, then lanes of k1
-    const uint32_t b0 = __reduce_min_sync(0xffffffffu, second ? 0xffffffffu : best);
-    const uint32_t b1 = __reduce_min_sync(0xffffffffu, second ? best : 0xffffffffu);
     const int bslot0 = __shfl_sync(0xffffffffu, m.bslot, 0);
     const int bslot1 = __shfl_sync(0xffffffffu, m.bslot, 31);
+    uint32_t b0 = __reduce_min_sync(0xffffffffu, second ? 0xffffffffu : best);
+    uint32_t b1 = __reduce_min_sync(0xffffffffu, second ? best : 0xffffffffu);
+    uint32_t r0 = 0, r1 = 0;
+    if (K64) {  // among the lanes holding the minimum SAD, the smallest rank
+      r0 = __reduce_min_sync(0xffffffffu, (!second && best == b0) ? best_rank : 0xffffffffu);
+      r1 = __reduce_min_sync(0xffffffffu, (second && best == b1) ? best_rank : 0xffffffffu);
+    }
     if (lane == 0) {
-      if (b0 != 0xffffffffu) atomicMin(&s_bkey[bslot0], b0);
-      if (k1 != k0 && b1 != 0xffffffffu) atomicMin(&s_bkey[bslot1], b1);
+      if (K64) {
+        if (b0 != 0xffffffffu) atomicMin(&s_bkey64[bslot0], ((unsigned long long)b0 << 32) | r0);
+        if (k1 != k0 && b1 != 0xffffffffu) atomicMin(&s_bkey64[bslot1], ((unsigned long long)b1 << 32) | r1);
+      } else {
+        if (b0 != 0xffffffffu) atomicMin(&s_bkey[bslot0], b0);
+        if (k1 != k0 && b1 != 0xffffffffu) atomicMin(&s_bkey[bslot1], b1);
+      }
       __threadfence_block();
       const int n0 = min(32, split);
       const uint32_t d0 = atomicAdd(&s_sdone[k0 % kStages], (uint32_t)n0);
@@ -392,6 +432,7 @@ static int pick_seg(int bs, int R) {
 struct TmaGeom {
   TmaSearchArgs a;
   int seg;
+  int k64;
   int box_w, box_h;
   size_t smem;
 };
@@ -401,25 +442,38 @@ static bool make_geom(int w, int h, int bs, int R, TmaGeom* g) {
   if (R < 1) return false;
   memset(g, 0, sizeof(*g));
   const int n = 2 * R + 1;
-  if (n * n > (bs >= 32 ? (1 << 14) : (1 << 16)) - 1) return false;  // spiral rank must fit the key's low bits
+  // the 32-bit key holds SAD << KS | rank; larger rank spaces use the 64-bit-key instantiations (16x16 and 32x32 only)
+  const bool k64 = n * n > (bs >= 32 ? (1 << 14) : (1 << 16)) - 1;
+  if (k64 && bs == 8) return false;
+  if ((long long)n * n > 0x7fffffffLL) return false;
   const int seg = pick_seg(bs, R);
   // staged box: starts at the 16-byte aligned column at or below (x2 - R); a lane reads words
   // (off + o) >> 2 ... + bs/4 inclusive, with off <= 15 and o <= 2R
   const int words = ((15 + 2 * R) >> 2) + bs / 4 + 1;
   // the row pitch is a template parameter of the kernel: round up to the next instantiated class
+  // (K64 kernels are instantiated for pitches 40 and 64 only)
   static const int kPitchClasses[6] = {16, 24, 32, 40, 48, 64};
-  int pww = 0;
+  int pww = 0, two_box = 0;
   for (int i = 0; i < 6 && !pww; ++i)
-    if (words <= kPitchClasses[i]) pww = kPitchClasses[i];
-  if (!pww) return false;
+    if (words <= kPitchClasses[i] && (!k64 || kPitchClasses[i] == 40 || kPitchClasses[i] == 64)) pww = kPitchClasses[i];
+  if (!pww) {
+    // wider than one 256-byte TMA box: two boxes of pitch pww overlapping by 4 words (K64 kernels only)
+    for (int i = 0; i < 6 && !pww; ++i)
+      if (2 * kPitchClasses[i] - 4 >= words && (kPitchClasses[i] == 40 || kPitchClasses[i] == 64)) pww = kPitchClasses[i];
+    if (!pww || bs == 8) return false;
+    two_box = 1;
+  }
+  const bool use_k64 = k64 || two_box;
   const int box_w = pww * 4;
   const int segs_total = (n + seg - 1) / seg;
   const int blk_bytes = bs * (bs >= 16 ? bs : 16);
   const size_t budget = 24 * 1024;  // per stage
   int spb = segs_total;
+  size_t one_box = 0;
   for (;;) {
     const int box_h = spb * seg + bs - 1;
-    const size_t win_bytes = (((size_t)box_h * box_w) + 127) / 128 * 128;
+    one_box = (((size_t)box_h * box_w) + 127) / 128 * 128;
+    const size_t win_bytes = one_box * (two_box ? 2 : 1);
     const size_t stage = win_bytes + ((blk_bytes + 127) / 128) * 128;
     if ((stage <= budget && box_h <= 256) || spb == 1) {
       if (stage > 64 * 1024 || box_h > 256) return false;
@@ -431,6 +485,7 @@ static bool make_geom(int w, int h, int bs, int R, TmaGeom* g) {
     --spb;
   }
   g->seg = seg;
+  g->k64 = use_k64 ? 1 : 0;
   g->box_w = box_w;
   g->a.w = w; g->a.h = h;
   g->a.gw = w / bs; g->a.gh = h / bs;
@@ -443,15 +498,17 @@ static bool make_geom(int w, int h, int bs, int R, TmaGeom* g) {
   g->a.pww = box_w / 4;
   g->a.box_bytes = g->box_h * box_w;
   g->a.blk_bytes = blk_bytes;
+  g->a.box1_word = two_box ? pww - 4 : 0;
+  g->a.box1_off_words = two_box ? (int)(one_box / 4) : 0;
   g->a.rank_off = kStages * g->a.stage_bytes;
-  g->smem = (size_t)g->a.rank_off + (((size_t)(n + seg) * n * 2 + 127) / 128) * 128;
+  g->smem = (size_t)g->a.rank_off + (use_k64 ? 0 : (((size_t)(n + seg) * n * 2 + 127) / 128) * 128);
   return true;
 }
 
-template <int BS, int SEG, int PWW>
+template <int BS, int SEG, int PWW, bool K64>
 static void launch_inst(const TmaSearchPlan& plan, const TmaSearchArgs& a, int grid, cudaStream_t s) {
-  cudaFuncSetAttribute(k_search_tma<BS, SEG, PWW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  k_search_tma<BS, SEG, PWW><<<grid, kThreads, plan.smem_bytes, s>>>(plan.map_win, plan.map_blk, a);
+  cudaFuncSetAttribute(k_search_tma<BS, SEG, PWW, K64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  k_search_tma<BS, SEG, PWW, K64><<<grid, kThreads, plan.smem_bytes, s>>>(plan.map_win, plan.map_blk, a);
 }
 
 int tma_search_plan(TmaSearchPlan* plan, const uint8_t* img1, const uint8_t* img2, int w, int h, int pitch,
@@ -496,11 +553,16 @@ void launch_search_tma(const TmaSearchPlan& plan, ImgView i1, ImgView i2, MvView
   int grid = sm_count * 2;
   if (grid > total) grid = total;
 #define BBME_CASE(BS_, SEG_, PWW_) \
-  if (plan.bs == BS_ && plan.seg == SEG_ && a.pww == PWW_) { launch_inst<BS_, SEG_, PWW_>(plan, a, grid, s); return; }
+  if (!g.k64 && plan.bs == BS_ && plan.seg == SEG_ && a.pww == PWW_) { launch_inst<BS_, SEG_, PWW_, false>(plan, a, grid, s); return; }
+#define BBME_CASE64(BS_, SEG_, PWW_) \
+  if (g.k64 && plan.bs == BS_ && plan.seg == SEG_ && a.pww == PWW_) { launch_inst<BS_, SEG_, PWW_, true>(plan, a, grid, s); return; }
 #define BBME_CASES(BS_, SEG_) \
   BBME_CASE(BS_, SEG_, 16) BBME_CASE(BS_, SEG_, 24) BBME_CASE(BS_, SEG_, 32) BBME_CASE(BS_, SEG_, 40) \
   BBME_CASE(BS_, SEG_, 48) BBME_CASE(BS_, SEG_, 64)
   BBME_CASES(8, 13) BBME_CASES(8, 11) BBME_CASES(16, 13) BBME_CASES(16, 11) BBME_CASES(32, 13) BBME_CASES(32, 11)
+  BBME_CASE64(16, 13, 40) BBME_CASE64(16, 13, 64) BBME_CASE64(16, 11, 40) BBME_CASE64(16, 11, 64)
+  BBME_CASE64(32, 13, 40) BBME_CASE64(32, 13, 64) BBME_CASE64(32, 11, 40) BBME_CASE64(32, 11, 64)
+#undef BBME_CASE64
 #undef BBME_CASES
 #undef BBME_CASE
 }

@@ -55,6 +55,33 @@ def test_search_tma_matches_oracle(gpu, oracle, bs, ss, pred_mode):
     assert st["search_kernel_used"] == 2  # TMA kernel ran
 
 
+@pytest.mark.parametrize("bs,ss,h,w", [(16, 272, 160, 224),   # +-128: two TMA boxes, 64-bit key (BASELINE config 5 geometry)
+                                      (16, 272, 448, 512),
+                                      (32, 160, 256, 320),   # 32x32, +-64: rank space beyond the 14-bit key
+                                      (32, 200, 256, 320),
+                                      (16, 216, 320, 384)])  # +-100: one 256-byte box, 16-bit ranks
+@pytest.mark.parametrize("pred_mode", ["zero", "small"])
+def test_search_tma_large_ranges(gpu, oracle, bs, ss, h, w, pred_mode):
+    f1, f2 = make_pair(h, w, 400 + bs + ss, shift=(9, -6), max_patch_shift=30)
+    rng = np.random.default_rng(ss + h)
+    pred = np.zeros((h // bs, w // bs, 2), np.int16) if pred_mode == "zero" else rng.integers(-20, 21, (h // bs, w // bs, 2)).astype(np.int16)
+    got, st = gpu.stage_search(f1, f2, bs, ss, pred, kernel=2)
+    want_dense, ost = oracle.search_level(f1, f2, bs, ss, blocks_to_dense(pred, bs, h, w))
+    want = dense_to_blocks(want_dense, bs)
+    assert st["search_kernel_used"] == 2
+    assert np.array_equal(got, want), describe_diff(got, want)
+    assert st["search_absdiffs"] == ost["search_absdiffs"]
+
+
+def test_search_large_range_ties(gpu, oracle):
+    # constant frames, +-128: every candidate ties; the 64-bit key must pick the first in-bounds spiral position
+    f = np.full((160, 224), 9, np.uint8)
+    pred = np.random.default_rng(1).integers(-30, 31, (10, 14, 2)).astype(np.int16)
+    got, _ = gpu.stage_search(f, f, 16, 272, pred, kernel=2)
+    want = dense_to_blocks(oracle.search_level(f, f, 16, 272, blocks_to_dense(pred, 16, 160, 224))[0], 16)
+    assert np.array_equal(got, want), describe_diff(got, want)
+
+
 @pytest.mark.parametrize("kind", ["constant", "noise"])
 @pytest.mark.parametrize("kernel", [1, 2])
 def test_search_tie_break_and_noise(gpu, oracle, kind, kernel):
