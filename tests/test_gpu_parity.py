@@ -4,7 +4,9 @@ import numpy as np
 import pytest
 
 import blockbasedmotionestimation_b200 as bb
-from helpers import blocks_to_dense, dense_to_blocks, describe_diff, make_pair, mv2_to_dense
+import os
+
+from helpers import blocks_to_dense, dense_to_blocks, describe_diff, make_pair, mv2_to_dense, up4
 
 pytestmark = pytest.mark.gpu
 
@@ -229,6 +231,39 @@ def test_plan_errors_are_loud():
 
 
 # ------------------------------------------------------------------------------------------ full size (BASELINE configs)
+def test_config0_rubberwhale_standin_default_parameters(oracle, tmp_path):
+    """BASELINE config 0: RubberWhale (584x388) through main()'s pipeline with the repo's defaults -- x4 bilinear
+    up-sampling, search_size 64 / block_size 32 / 4 levels (main_class.cpp:19-21,32-33), strip padding, every 4th pixel,
+    MV / 4 (:58-70), AEE against gt-flow (:78-82).  The PNG frames are not in the reference tree, so the pair is the
+    committed stand-in (tests/golden/make_rubberwhale_standin.py: a texture warped by the real ground-truth flow)."""
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rubberwhale_standin.npz"))
+    gt = d["gt"]
+    im1, im2 = up4(d["frame10"]), up4(d["frame11"])
+    ss, bs = [64, 64, 64, 64], [32, 32, 32, 32]
+    want, ost = oracle.estimate(im1, im2, ss, bs, 2)
+    mf = bb.MF(im1, im2, ss, bs, 4, collect_stats=True)
+    assert (mf.padded_width, mf.padded_height, mf.padding_x, mf.padding_y) == (2560, 1792, 112, 120)
+    got = mf.calcMotionBlockMatching()
+    st = mf.stats()
+    shape = mf._est.shape
+    mf.close()
+    assert np.array_equal(got, want), describe_diff(got, want)
+    assert st["search_absdiffs"] == ost["search_absdiffs"]
+    fl = bb.Flow()
+    sub = fl.StripAndSubsample(got, shape, 4)
+    assert sub.shape == gt.shape
+    aee = fl.CalculateMSE(gt, sub)
+    px, py = shape["padding_x"], shape["padding_y"]
+    sub_oracle = np.ascontiguousarray(want[py:shape["padded_height"] - py:4, px:shape["padded_width"] - px:4] / 4.0)
+    assert aee == oracle.aee(gt, sub_oracle)
+    assert aee < 0.25, aee  # sanity: the stand-in's motion IS the ground truth, quarter-pel vectors should be close
+    out = tmp_path / "rubberwhale.flo"
+    fl.WriteFlowFile(sub, out)
+    assert np.array_equal(fl.ReadFlowFile(out), sub)
+    print(f"RubberWhale stand-in: AEE {aee:.6f} px over gt-known pixels")
+
+
+
 def test_config2_1080p_matches_oracle(oracle):
     """BASELINE config 2: 1920x1080, 16x16 blocks, +-32 (search_size 80), 3 levels -- the oracle takes ~4 s."""
     h, w, ss, bs = 1080, 1920, [80, 80, 80], [16, 16, 16]

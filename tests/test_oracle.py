@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import make_pair
+from helpers import make_pair, up4
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = os.path.join(HERE, "golden")
@@ -154,3 +154,17 @@ def test_flo_gt_files_roundtrip_byte_identical(oracle, tmp_path):
         out = tmp_path / (seq + ".flo")
         oracle.flo_write(out, gt)
         assert open(out, "rb").read() == raw
+
+
+def test_config0_rubberwhale_standin_on_the_oracle(oracle):
+    """main()'s pipeline (main_class.cpp:19-21,32-33,58-82) on the committed RubberWhale stand-in: pins the oracle's
+    work counters (6.36 G search / 0.542 G regularisation abs-diffs) and the sanity AEE."""
+    d = np.load(os.path.join(GOLD, "rubberwhale_standin.npz"))
+    flow, st = oracle.estimate(up4(d["frame10"]), up4(d["frame11"]), [64] * 4, [32] * 4, 2)
+    assert flow.shape == (1792, 2560, 2)
+    assert (st["search_absdiffs"], st["reg_absdiffs"]) == (6362474496, 542256000)
+    assert (st["search_sad_calls"], st["reg_sad_calls"]) == (6213354, 36426318)
+    sub = np.ascontiguousarray(flow[120:1792 - 120:4, 112:2560 - 112:4] / 4.0)
+    assert sub.shape == d["gt"].shape
+    aee = oracle.aee(d["gt"], sub)
+    assert aee == pytest.approx(0.13334927018152679, rel=0, abs=1e-9)
