@@ -34,6 +34,7 @@ struct Slot {
   uint32_t* stamp = nullptr;
   uint32_t* ctr = nullptr;
   unsigned long long* counters = nullptr;  // [0] candidates, [1] absdiffs
+  uint32_t* hist = nullptr;                // BBME_FIX_HIST=1: kHistSweeps x 64 words (RegArgs::hist)
   float* out = nullptr;
   TmaSearchPlan tma[kMaxLevels];
   std::vector<cudaEvent_t> ev;
@@ -41,6 +42,7 @@ struct Slot {
   int last_n = 0;
 };
 
+constexpr int kHistSweeps = 256;
 enum { TAG_PYR = 0, TAG_SEARCH = 1, TAG_REG = 2, TAG_OTHER = 3, TAG_BEGIN = 4 };
 
 }  // namespace
@@ -200,6 +202,7 @@ int run_chunk(bbme_ctx* c, Slot& s, int n, const uint8_t* d_in1, const uint8_t* 
   const bbme_shape& sh = c->shape;
   const int L = sh.num_levels;
   cudaStream_t st = s.stream;
+  int sweep_id = 0;
   s.last_n = n > s.last_n ? n : s.last_n;
   mark(c, s, TAG_BEGIN);
   // ---- MF::MF: pad + Gaussian pyramid (motion_framework.cpp:57-106)
@@ -263,6 +266,8 @@ int run_chunk(bbme_ctx* c, Slot& s, int n, const uint8_t* d_in1, const uint8_t* 
         ra.stamp = s.stamp;
         ra.wl_plane = c->cap[0];
         ra.ctr = s.ctr;
+        ra.hist = (s.hist && sweep_id < kHistSweeps) ? s.hist + 64 * sweep_id : nullptr;
+        ++sweep_id;
         // with few pairs in flight the per-pair tail loop leaves most SMs idle: run the first (largest) rounds grid-wide
         const int gr = c->grid_rounds >= 0 ? c->grid_rounds : (n >= 96 ? 0 : 3);
         launch_reg_full(ra, n, st);
@@ -316,6 +321,19 @@ int collect_after_sync(bbme_ctx* c) {
         c->stats.reserved += ctr[(size_t)p * kCtrWords + CTR_TAIL_BLOCKS];
       }
       s.last_n = 0;
+    }
+  }
+  for (Slot& s : c->slots) {
+    if (!s.hist) continue;
+    std::vector<uint32_t> hh((size_t)kHistSweeps * 64);
+    CUDA_TRY(c, cudaMemcpy(hh.data(), s.hist, hh.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CUDA_TRY(c, cudaMemset(s.hist, 0, hh.size() * sizeof(uint32_t)));
+    for (int sw = 0; sw < kHistSweeps; ++sw) {
+      const uint32_t* q = &hh[(size_t)sw * 64];
+      if (!q[0] && !q[63]) continue;
+      fprintf(stderr, "fixhist sweep %d listed %u maxrounds %u sumrounds %u :", sw, q[0], q[62], q[63]);
+      for (int r = 0; r < 60 && q[2 + r]; ++r) fprintf(stderr, " %u", q[2 + r]);
+      fprintf(stderr, "\n");
     }
   }
   c->stats.search_launches = c->search_launches;
@@ -465,6 +483,7 @@ int bbme_plan(bbme_ctx* c, int width, int height, int num_levels, const int* sea
         (rc = dev_alloc(c, &s.ctr, n * kCtrWords, true)) || (rc = dev_alloc(c, &s.counters, (size_t)2, true)) ||
         (rc = dev_alloc(c, &s.out, n * c->out_plane, false)))
       return rc;
+    if (getenv("BBME_FIX_HIST") && (rc = dev_alloc(c, &s.hist, (size_t)kHistSweeps * 64, true))) return rc;
     for (int l = 0; l < L; ++l) {
       memset(&s.tma[l], 0, sizeof(s.tma[l]));
       if (o.search_kernel == 1) continue;

@@ -292,10 +292,13 @@ void launch_export_compact(const short2* mv2, int gw2, int gh2, size_t mv_plane,
 // Energy (:607) is float32 and un-fused: (float)SAD + ((lambda * (float)mult) * S); S is a sum of
 // integer-valued floats (< 2^24, exact), so it is accumulated in int and converted once.
 //
-// Small blocks (2x2, 4x4: 95 % of all block evaluations) are evaluated by one thread, branch-free: all nine slots
-// are always computed (missing neighbours hold a copy of C and are masked out of the argmin; their contribution to
-// the smoothness sums is removed arithmetically), so a warp never diverges; the only branch is warp-uniform (every
-// lane's nine candidates identical -> nothing can change).
+// Every evaluator is branch-free over the nine slots: all nine candidate windows are addressed first and their
+// loads issued together (missing neighbours and out-of-image candidates read the block's own position and are masked
+// out of the argmin), so one evaluation costs one memory round trip instead of nine dependent ones -- these kernels
+// are latency-bound (the candidate windows of a 128-pair chunk do not fit the L2).
+//
+// Small blocks (2x2, 4x4: 95 % of all block evaluations) are evaluated by one thread; the only branch is
+// warp-uniform (every lane's nine candidates identical -> nothing can change).
 template <int BS>  // 2 or 4
 __device__ __forceinline__ short2 reg_eval_small(const RegArgs& a, int pair, const short2* __restrict__ O,
                                                  const short2* P, int bx, int by, bool live) {
@@ -402,38 +405,94 @@ __device__ __forceinline__ short2 reg_eval_small(const RegArgs& a, int pair, con
   return r;
 }
 
-//
-// A block is evaluated by a TEAM of adjacent lanes (1 for block sizes 2 and 4, min(bs, 32) above): every lane takes
-// bs / TEAM rows of each candidate's SAD and the partial sums are combined with xor-shuffles inside the team, so
-// the latency of one evaluation no longer grows with the block area (the fix-up rounds are latency-bound).
+// Blocks of 8x8 and larger are evaluated by a TEAM of adjacent lanes (8 for 8x8, 16 for 16x16, 32 above): a lane
+// takes one block row (32x32 and larger: bs/32 rows, 16 bytes at a time), loads its slice of all nine candidate
+// windows at once, and the partial SADs are combined with xor-shuffles inside the team; every lane of the team ends
+// up with the same nine energies and the same winner.
 template <int TEAM>
-__device__ __forceinline__ short2 reg_eval(const RegArgs& a, int pair, const short2* __restrict__ O,
-                                           const short2* P, int bx, int by, int tl, uint32_t team_mask) {
+__device__ __forceinline__ short2 reg_eval_team(const RegArgs& a, int pair, const short2* __restrict__ O,
+                                                const short2* P, int bx, int by, int tl, uint32_t team_mask) {
   const int gw = a.gw, gh = a.gh, bs = a.bs;
   const int idx = by * gw + bx;
   const bool up = by > 0, dn = by < gh - 1, lf = bx > 0, rt = bx < gw - 1;
+  const short2 c0 = O[idx];
   short2 c[9];
-  uint32_t mask = 1u;
-  c[0] = O[idx];
-#pragma unroll
-  for (int i = 1; i < 9; ++i) c[i] = c[0];
-  if (lf) { c[1] = P[idx - 1]; mask |= 1u << 1; }
-  if (rt) { c[2] = O[idx + 1]; mask |= 1u << 2; }
-  if (dn && rt) { c[3] = O[idx + gw + 1]; mask |= 1u << 3; }
-  if (up && lf) { c[4] = P[idx - gw - 1]; mask |= 1u << 4; }
-  if (up && rt) { c[5] = P[idx - gw + 1]; mask |= 1u << 5; }
-  if (up) { c[6] = P[idx - gw]; mask |= 1u << 6; }
-  if (dn) { c[7] = O[idx + gw]; mask |= 1u << 7; }
-  if (dn && lf) { c[8] = O[idx + gw - 1]; mask |= 1u << 8; }
+  c[0] = c0;
+  c[1] = lf ? P[idx - 1] : c0;
+  c[2] = rt ? O[idx + 1] : c0;
+  c[3] = (dn && rt) ? O[idx + gw + 1] : c0;
+  c[4] = (up && lf) ? P[idx - gw - 1] : c0;
+  c[5] = (up && rt) ? P[idx - gw + 1] : c0;
+  c[6] = up ? P[idx - gw] : c0;
+  c[7] = dn ? O[idx + gw] : c0;
+  c[8] = (dn && lf) ? O[idx + gw - 1] : c0;
+  const uint32_t vmask = 1u | (lf ? 2u : 0u) | (rt ? 4u : 0u) | ((dn && rt) ? 8u : 0u) | ((up && lf) ? 16u : 0u) |
+                         ((up && rt) ? 32u : 0u) | (up ? 64u : 0u) | (dn ? 128u : 0u) | ((dn && lf) ? 256u : 0u);
 
-  // all candidates identical -> every energy is equal -> index 0 wins (:653-659)
-  const uint32_t k0 = pack_mv(c[0]);
-  bool all_same = true;
+  const int x = bx * bs, y = by * bs;
+  const int w = a.i1.w, h = a.i1.h, pitch = a.i1.pitch;
+  const uint8_t* blk = a.i1.p + (size_t)pair * a.i1.plane + (size_t)y * pitch + x;
+  const uint8_t* ref = a.i2.p + (size_t)pair * a.i2.plane;
+  // candidate windows: out-of-image ones (:578-582) read the block's own position and get FLT_MAX below
+  uint32_t inb = 0;
+  const uint8_t* bp[9];
 #pragma unroll
-  for (int i = 1; i < 9; ++i) all_same = all_same && (pack_mv(c[i]) == k0);  // dropped slots hold c[0]
-  if (all_same) return c[0];
+  for (int i = 0; i < 9; ++i) {
+    const int px = x + c[i].x, py = y + c[i].y;
+    const bool ok = (unsigned)px <= (unsigned)(w - bs) && (unsigned)py <= (unsigned)(h - bs);
+    inb |= ok ? (1u << i) : 0u;
+    bp[i] = ref + (size_t)(ok ? py : y) * pitch + (ok ? px : x);
+  }
+  uint32_t sad[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) sad[i] = 0u;
+  if (TEAM == 8) {
+    const size_t ro = (size_t)tl * pitch;
+    const uint2 A = __ldg(reinterpret_cast<const uint2*>(blk + ro));
+    uint32_t wv[9][3], sh[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const uintptr_t ab = reinterpret_cast<uintptr_t>(bp[i] + ro);
+      const uint32_t* bw = reinterpret_cast<const uint32_t*>(ab & ~(uintptr_t)3);
+      sh[i] = (uint32_t)(ab & 3) * 8u;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) wv[i][k] = __ldg(bw + k);
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+      sad[i] = sad4(A.y, __funnelshift_r(wv[i][1], wv[i][2], sh[i]), sad4(A.x, __funnelshift_r(wv[i][0], wv[i][1], sh[i]), 0u));
+  } else {
+    // 16 bytes of one row per step; TEAM == 16: one step, TEAM == 32: (bs / 32) rows x (bs / 16) column chunks
+    const int rows = TEAM == 16 ? 1 : bs / 32;
+    const int chunks = TEAM == 16 ? 1 : bs / 16;
+    for (int rr = 0; rr < rows; ++rr) {
+      for (int ch = 0; ch < chunks; ++ch) {
+        const size_t ro = (size_t)(rr * TEAM + tl) * pitch + ch * 16;
+        const uint4 A = __ldg(reinterpret_cast<const uint4*>(blk + ro));
+        uint32_t wv[9][5], sh[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          const uintptr_t ab = reinterpret_cast<uintptr_t>(bp[i] + ro);
+          const uint32_t* bw = reinterpret_cast<const uint32_t*>(ab & ~(uintptr_t)3);
+          sh[i] = (uint32_t)(ab & 3) * 8u;
+#pragma unroll
+          for (int k = 0; k < 5; ++k) wv[i][k] = __ldg(bw + k);
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          uint32_t s = sad[i];
+          s = sad4(A.x, __funnelshift_r(wv[i][0], wv[i][1], sh[i]), s);
+          s = sad4(A.y, __funnelshift_r(wv[i][1], wv[i][2], sh[i]), s);
+          s = sad4(A.z, __funnelshift_r(wv[i][2], wv[i][3], sh[i]), s);
+          s = sad4(A.w, __funnelshift_r(wv[i][3], wv[i][4], sh[i]), s);
+          sad[i] = s;
+        }
+      }
+    }
+  }
 
-  // smoothness: S_i = sum over gathered candidates k of |c_k.x - c_i.x| + |c_k.y - c_i.y|  (:637-641)
+  // smoothness: S_i = sum over gathered candidates k of |c_k.x - c_i.x| + |c_k.y - c_i.y|  (:637-641); computed while
+  // the window loads are in flight
   int S[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) S[i] = 0;
@@ -442,74 +501,33 @@ __device__ __forceinline__ short2 reg_eval(const RegArgs& a, int pair, const sho
 #pragma unroll
     for (int k = i + 1; k < 9; ++k) {
       const int d = abs((int)c[i].x - (int)c[k].x) + abs((int)c[i].y - (int)c[k].y);
-      const bool both = ((mask >> i) & (mask >> k) & 1u) != 0u;
+      const bool both = ((vmask >> i) & (vmask >> k) & 1u) != 0u;
       S[i] += both ? d : 0;
       S[k] += both ? d : 0;
     }
   }
-
-  const int x = bx * bs, y = by * bs;
-  const int w = a.i1.w, h = a.i1.h, pitch = a.i1.pitch;
-  const uint8_t* blk = a.i1.p + (size_t)pair * a.i1.plane + (size_t)y * pitch + x;
-  const uint8_t* ref = a.i2.p + (size_t)pair * a.i2.plane;
-  const int rows = TEAM > 1 ? bs / TEAM : bs;  // rows of the block this lane sums
-  const int r0 = TEAM > 1 ? tl * rows : 0;
+#pragma unroll
+  for (int off = TEAM / 2; off > 0; off >>= 1) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) sad[i] += __shfl_xor_sync(team_mask, sad[i], off);
+  }
   float best = 0.f;
   int best_i = 0;
 #pragma unroll
   for (int i = 0; i < 9; ++i) {
-    if (!((mask >> i) & 1u)) continue;
-    // a candidate equal to an earlier gathered one has the identical energy and cannot win by strict '<'
-    bool dup = false;
-#pragma unroll
-    for (int j = 0; j < i; ++j) dup = dup || (((mask >> j) & 1u) && pack_mv(c[j]) == pack_mv(c[i]));
-    if (dup) continue;
-    const int px = x + c[i].x, py = y + c[i].y;
-    float e;
-    if (px < 0 || px > w - bs || py < 0 || py > h - bs) {
-      e = FLT_MAX;  // :578-582
+    const float e = ((inb >> i) & 1u) ? __fadd_rn(__uint2float_rn(sad[i]), __fmul_rn(a.lm, __int2float_rn(S[i]))) : FLT_MAX;
+    if (i == 0) {
+      best = e;
     } else {
-      uint32_t sad;
-      if (TEAM == 1) {
-        sad = sad_block_unaligned(blk, ref + (size_t)py * pitch + px, pitch, bs);
-      } else {
-        sad = 0;
-        const int words = bs >> 2;
-        for (int r = r0; r < r0 + rows; ++r) {
-          const uint32_t* aw = reinterpret_cast<const uint32_t*>(blk + (size_t)r * pitch);
-          const uintptr_t ab = reinterpret_cast<uintptr_t>(ref + (size_t)(py + r) * pitch + px);
-          const uint32_t* bw = reinterpret_cast<const uint32_t*>(ab & ~(uintptr_t)3);
-          const uint32_t sh = (uint32_t)(ab & 3) * 8u;
-          uint32_t w0 = __ldg(bw);
-          for (int k = 0; k < words; ++k) {
-            const uint32_t w1 = __ldg(bw + k + 1);
-            sad = sad4(__ldg(aw + k), __funnelshift_r(w0, w1, sh), sad);
-            w0 = w1;
-          }
-        }
-#pragma unroll
-        for (int off = TEAM / 2; off > 0; off >>= 1) sad += __shfl_xor_sync(team_mask, sad, off);
-      }
-      e = __fadd_rn(__uint2float_rn(sad), __fmul_rn(a.lm, __int2float_rn(S[i])));
+      const bool take = ((vmask >> i) & 1u) && (e < best);  // strict '<' from index 1 (:653-659)
+      best = take ? e : best;
+      best_i = take ? i : best_i;
     }
-    if (i == 0) { best = e; best_i = 0; }
-    else if (e < best) { best = e; best_i = i; }
   }
-  short2 r = c[0];
+  short2 r = c0;
 #pragma unroll
   for (int i = 1; i < 9; ++i) r = (best_i == i) ? c[i] : r;
   return r;
-}
-
-// Blocks whose "pred" neighbour is block (bx,by): its right, lower-left, lower and lower-right neighbours.
-template <typename Push>
-__device__ __forceinline__ void for_each_dependent(int bx, int by, int gw, int gh, Push push) {
-  if (bx + 1 < gw) push(by * gw + bx + 1);
-  if (by + 1 < gh) {
-    if (bx > 0) push((by + 1) * gw + bx - 1);
-    push((by + 1) * gw + bx);
-    if (bx + 1 < gw) push((by + 1) * gw + bx + 1);
-  }
 }
 
 // TEAM == 1 evaluates 2x2 blocks, TEAM == 2 is the tag for "one thread per 4x4 block" (TEAMSZ below is 1 for both)
@@ -521,43 +539,122 @@ __device__ __forceinline__ short2 reg_eval_any(const RegArgs& a, int pair, const
   } else if (TEAM == 2) {
     return reg_eval_small<4>(a, pair, O, P, bx, by, live);
   } else {
-    return reg_eval<TEAM>(a, pair, O, P, bx, by, tl, team_mask);
+    return reg_eval_team<TEAM>(a, pair, O, P, bx, by, tl, team_mask);
   }
 }
 
+// A block that changed invalidates the evaluations of the blocks that read it as a "pred" neighbour: its right,
+// lower-left, lower and lower-right neighbours.  They are appended to the next round's work list, de-duplicated by an
+// epoch stamp per block.  Called by all 32 lanes of a warp together: the four stamp exchanges of a lane are issued
+// back to back (independent atomics, one round trip), and the list slots of the whole warp are reserved with ONE
+// atomicAdd (a per-entry atomicAdd on the pair's counter serialises in the L2).
+__device__ __forceinline__ void push_dependents(bool changed, int bx, int by, int gw, int gh, uint32_t* stamp,
+                                                uint32_t ep, uint32_t* list, uint32_t* count) {
+  const int lane = threadIdx.x & 31;
+  int d[4];
+  d[0] = by * gw + bx + 1;
+  d[1] = (by + 1) * gw + bx - 1;
+  d[2] = (by + 1) * gw + bx;
+  d[3] = (by + 1) * gw + bx + 1;
+  const bool rt = bx + 1 < gw, dn = by + 1 < gh;
+  const bool ex[4] = {changed && rt, changed && dn && bx > 0, changed && dn, changed && dn && rt};
+  uint32_t old[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) old[j] = ex[j] ? atomicExch(&stamp[d[j]], ep) : ep;
+  int k = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) k += (old[j] != ep) ? 1 : 0;
+  const uint32_t any = __ballot_sync(0xffffffffu, k > 0);
+  if (any == 0u) return;
+  int incl = k;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  uint32_t base = 0;
+  if (lane == 31) base = atomicAdd(count, (uint32_t)incl);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  uint32_t pos = base + (uint32_t)(incl - k);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (old[j] != ep) list[pos++] = (uint32_t)d[j];
+}
+
 // Pass 1 of a sweep (a Jacobi step: every block evaluated with the OLD field in all nine slots), in two kernels:
-//  k_reg_classify  one thread per block, ~20 registers, full occupancy: blocks whose nine candidates are identical
-//                  keep their vector (all energies equal, index 0 wins, :653-659) and are done; the others are
-//                  compacted into the evaluation list (warp-aggregated append, so neighbours stay neighbours).
-//                  On real fields 80-96 % of the 2x2 / 4x4 blocks are of the first kind.
-//  k_reg_eval      dense evaluation of the listed blocks; blocks whose value changed enqueue their dependents
-//                  (they may have used a stale "pred" value) for the fix-up rounds.
+//  k_reg_classify  copies O to Y and lists the blocks whose nine candidates are not all identical.  A block whose
+//                  candidates are identical keeps its vector (all energies equal, index 0 wins, :653-659); on real
+//                  fields 80-96 % of the 2x2 / 4x4 blocks are of that kind.  One thread handles four horizontally
+//                  adjacent blocks: three 128-bit row loads + six halo entries instead of 36 scalar loads; the list
+//                  slots of a warp are reserved with one atomicAdd, so neighbours stay neighbours in the list.
+//  k_reg_eval      evaluation of the listed blocks by a fixed-size grid that strides over the list; blocks whose
+//                  value changed enqueue their dependents (they may have used a stale "pred" value) for the rounds.
+__global__ void __launch_bounds__(256) k_reg_classify4(RegArgs a) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pair = blockIdx.y;
+  const int gw = a.gw, gh = a.gh, gw4 = gw >> 2;
+  const int lane = threadIdx.x & 31;
+  const bool live = t < gw4 * gh;
+  const uint32_t* __restrict__ O = reinterpret_cast<const uint32_t*>(a.O + (size_t)pair * a.mv_plane);
+  uint32_t work = 0;
+  int i0 = 0;
+  if (live) {
+    const int tx = t % gw4, by = t / gw4;
+    const int bx = tx * 4;
+    i0 = by * gw + bx;
+    // clamped coordinates: a clamped neighbour is the block itself or another neighbour, so the test is unchanged
+    const int ru = max(by - 1, 0) * gw, rm = by * gw, rd = min(by + 1, gh - 1) * gw;
+    const int cl = max(bx - 1, 0), cr = min(bx + 4, gw - 1);
+    const uint4 U = *reinterpret_cast<const uint4*>(O + ru + bx);
+    const uint4 M = *reinterpret_cast<const uint4*>(O + rm + bx);
+    const uint4 D = *reinterpret_cast<const uint4*>(O + rd + bx);
+    const uint32_t u[6] = {O[ru + cl], U.x, U.y, U.z, U.w, O[ru + cr]};
+    const uint32_t m[6] = {O[rm + cl], M.x, M.y, M.z, M.w, O[rm + cr]};
+    const uint32_t d[6] = {O[rd + cl], D.x, D.y, D.z, D.w, O[rd + cr]};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t k0 = m[j + 1];
+      const bool same = u[j] == k0 && u[j + 1] == k0 && u[j + 2] == k0 && m[j] == k0 && m[j + 2] == k0 && d[j] == k0 &&
+                        d[j + 1] == k0 && d[j + 2] == k0;
+      work |= same ? 0u : (1u << j);
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(a.Y + (size_t)pair * a.mv_plane) + i0) = M;
+  }
+  const int k = __popc(work);
+  if (__ballot_sync(0xffffffffu, k > 0) == 0u) return;
+  int incl = k;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  uint32_t base = 0;
+  if (lane == 31) base = atomicAdd(&a.ctr[(size_t)pair * kCtrWords + CTR_COUNT_EVAL], (uint32_t)incl);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  uint32_t* list = a.list1 + (size_t)pair * a.wl_plane + base + (uint32_t)(incl - k);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if ((work >> j) & 1u) *list++ = (uint32_t)(i0 + j);
+}
+
+// grids whose width is not a multiple of four (only the coarsest stages of small images): one thread per block
 __global__ void __launch_bounds__(256) k_reg_classify(RegArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int pair = blockIdx.y;
   const int gw = a.gw, gh = a.gh;
   const bool live = i < gw * gh;
-  const short2* __restrict__ O = a.O + (size_t)pair * a.mv_plane;
+  const uint32_t* __restrict__ O = reinterpret_cast<const uint32_t*>(a.O + (size_t)pair * a.mv_plane);
   bool work = false;
   if (live) {
     const int bx = i % gw, by = i / gw;
-    const bool up = by > 0, dn = by < gh - 1, lf = bx > 0, rt = bx < gw - 1;
-    const short2 c0 = O[i];
-    const uint32_t k0 = pack_mv(c0);
+    const int ru = max(by - 1, 0) * gw, rm = by * gw, rd = min(by + 1, gh - 1) * gw;
+    const int cl = max(bx - 1, 0), cr = min(bx + 1, gw - 1);
+    const uint32_t k0 = O[i];
+    const uint32_t v[8] = {O[ru + cl], O[ru + bx], O[ru + cr], O[rm + cl], O[rm + cr], O[rd + cl], O[rd + bx], O[rd + cr]};
     bool same = true;
-    if (lf) same = same && pack_mv(O[i - 1]) == k0;
-    if (rt) same = same && pack_mv(O[i + 1]) == k0;
-    if (up) {
-      same = same && pack_mv(O[i - gw]) == k0;
-      if (lf) same = same && pack_mv(O[i - gw - 1]) == k0;
-      if (rt) same = same && pack_mv(O[i - gw + 1]) == k0;
-    }
-    if (dn) {
-      same = same && pack_mv(O[i + gw]) == k0;
-      if (lf) same = same && pack_mv(O[i + gw - 1]) == k0;
-      if (rt) same = same && pack_mv(O[i + gw + 1]) == k0;
-    }
-    if (same) a.Y[(size_t)pair * a.mv_plane + i] = c0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) same = same && v[j] == k0;
+    reinterpret_cast<uint32_t*>(a.Y + (size_t)pair * a.mv_plane)[i] = k0;
     work = !same;
   }
   const uint32_t m = __ballot_sync(0xffffffffu, work);
@@ -572,36 +669,33 @@ __global__ void __launch_bounds__(256) k_reg_classify(RegArgs a) {
 }
 
 template <int TEAM>
-__global__ void __launch_bounds__(128, TEAM <= 2 ? 4 : 1) k_reg_eval(RegArgs a) {
+__global__ void __launch_bounds__(128, TEAM <= 2 ? 4 : 2) k_reg_eval(RegArgs a) {
   constexpr int TEAMSZ = TEAM <= 2 ? 1 : TEAM;
+  constexpr int TPW = 32 / TEAMSZ;  // teams per warp
   const int pair = blockIdx.y;
   uint32_t* ctr = a.ctr + (size_t)pair * kCtrWords;
   const uint32_t cnt = ctr[CTR_COUNT_EVAL];
-  const uint32_t first = (uint32_t)(blockIdx.x * blockDim.x) / TEAMSZ;
-  if (first >= cnt) return;  // the grid is sized for "every block listed"
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t e = t / TEAMSZ;
-  const int tl = (int)(t % TEAMSZ);
-  const bool live = e < cnt;
-  if (!live) {
-    if (TEAMSZ > 1) return;  // whole teams leave together
-    e = cnt - 1;             // one thread per block: keep the warp converged
-  }
+  if (cnt == 0) return;
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t team = gtid / TEAMSZ, nteams = gridDim.x * blockDim.x / TEAMSZ;
+  const int tl = (int)(gtid % TEAMSZ);
   const uint32_t team_mask = TEAMSZ >= 32 ? 0xffffffffu : (((1u << TEAMSZ) - 1u) << ((threadIdx.x & 31) / TEAMSZ * TEAMSZ));
   const short2* O = a.O + (size_t)pair * a.mv_plane;
   short2* Y = a.Y + (size_t)pair * a.mv_plane;
-  const int i = (int)a.list1[(size_t)pair * a.wl_plane + e];
-  const int bx = i % a.gw, by = i / a.gw;
-  const short2 nv = reg_eval_any<TEAM>(a, pair, O, O, bx, by, tl, team_mask, live);
-  if (tl != 0 || !live) return;
-  Y[i] = nv;
-  if (pack_mv(nv) != pack_mv(O[i])) {
-    const uint32_t ep = ctr[CTR_EPOCH] + 1u;
-    uint32_t* stamp = a.stamp + (size_t)pair * a.wl_plane;
-    uint32_t* list = a.list0 + (size_t)pair * a.wl_plane;
-    for_each_dependent(bx, by, a.gw, a.gh, [&](int d) {
-      if (atomicExch(&stamp[d], ep) != ep) list[atomicAdd(&ctr[CTR_COUNT0], 1u)] = (uint32_t)d;
-    });
+  const uint32_t* lc = a.list1 + (size_t)pair * a.wl_plane;
+  uint32_t* stamp = a.stamp + (size_t)pair * a.wl_plane;
+  uint32_t* ln = a.list0 + (size_t)pair * a.wl_plane;
+  const uint32_t ep = ctr[CTR_EPOCH] + 1u;
+  const uint32_t limit = (cnt + TPW - 1) / TPW * TPW;  // whole warps iterate together
+  for (uint32_t e = team; e < limit; e += nteams) {
+    const bool live = e < cnt;
+    const int i = (int)lc[live ? e : cnt - 1];
+    const int bx = i % a.gw, by = i / a.gw;
+    const short2 nv = reg_eval_any<TEAM>(a, pair, O, O, bx, by, tl, team_mask, live);
+    const bool lead = tl == 0 && live;
+    const bool changed = lead && pack_mv(nv) != pack_mv(O[i]);
+    if (changed) Y[i] = nv;  // k_reg_classify copied O to Y
+    push_dependents(changed, bx, by, a.gw, a.gh, stamp, ep, ln, &ctr[CTR_COUNT0]);
   }
 }
 
@@ -613,14 +707,15 @@ __global__ void __launch_bounds__(128, TEAM <= 2 ? 4 : 1) k_reg_eval(RegArgs a) 
 // after the next barrier / kernel boundary.  Only the path to the fixed point varies, not the result.
 //
 // Round r reads list[r & 1] (count in counter r % 3), appends to list[(r + 1) & 1] (counter (r + 1) % 3, stamp
-// epoch + 2 + r) and clears counter (r + 2) % 3 for the round after.  The first rounds are the big ones and run as
-// grid-wide kernels over all pairs (k_reg_round); the tail, where rounds are short and latency-bound, runs as one
-// CTA per pair that loops until its list is empty (k_reg_fix).
+// epoch + 2 + r) and clears counter (r + 2) % 3 for the round after.  With few pairs in flight the first rounds (the
+// big ones) run as grid-wide kernels over all pairs (k_reg_round); the tail, where rounds are short and
+// latency-bound, runs as one CTA per pair that loops until its list is empty (k_reg_fix).
 __device__ __forceinline__ int ctr_index(int k) { return k == 2 ? CTR_COUNT2 : k; }
 
 template <int TEAM>
 __global__ void __launch_bounds__(256, TEAM <= 2 ? 2 : 1) k_reg_round(RegArgs a, int r) {
   constexpr int TEAMSZ = TEAM <= 2 ? 1 : TEAM;
+  constexpr int TPW = 32 / TEAMSZ;
   const int pair = blockIdx.y;
   uint32_t* ctr = a.ctr + (size_t)pair * kCtrWords;
   const uint32_t cnt = ctr[ctr_index(r % 3)];
@@ -639,24 +734,22 @@ __global__ void __launch_bounds__(256, TEAM <= 2 ? 2 : 1) k_reg_round(RegArgs a,
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t team = gtid / TEAMSZ, tl = gtid % TEAMSZ, nteams = gridDim.x * blockDim.x / TEAMSZ;
   const uint32_t team_mask = TEAMSZ >= 32 ? 0xffffffffu : (((1u << TEAMSZ) - 1u) << ((threadIdx.x & 31) / TEAMSZ * TEAMSZ));
-  const uint32_t limit = TEAMSZ == 1 ? ((cnt + 31u) & ~31u) : cnt;
+  const uint32_t limit = (cnt + TPW - 1) / TPW * TPW;
   for (uint32_t e = team; e < limit; e += nteams) {
     const bool live = e < cnt;
     const int b = (int)lc[live ? e : cnt - 1];
     const int bx = b % a.gw, by = b / a.gw;
     const short2 nv = reg_eval_any<TEAM>(a, pair, O, Y, bx, by, (int)tl, team_mask, live);
-    if (tl == 0 && live && pack_mv(nv) != pack_mv(Y[b])) {
-      Y[b] = nv;
-      for_each_dependent(bx, by, a.gw, a.gh, [&](int d) {
-        if (atomicExch(&stamp[d], ep) != ep) ln[atomicAdd(next_count, 1u)] = (uint32_t)d;
-      });
-    }
+    const bool changed = tl == 0 && live && pack_mv(nv) != pack_mv(Y[b]);
+    if (changed) Y[b] = nv;
+    push_dependents(changed, bx, by, a.gw, a.gh, stamp, ep, ln, next_count);
   }
 }
 
 template <int TEAM>
-__global__ void __launch_bounds__(TEAM <= 2 ? 512 : 1024) k_reg_fix(RegArgs a, int r0) {
+__global__ void __launch_bounds__(512) k_reg_fix(RegArgs a, int r0) {
   constexpr int TEAMSZ = TEAM <= 2 ? 1 : TEAM;
+  constexpr int TPW = 32 / TEAMSZ;
   const int pair = blockIdx.x;
   const short2* O = a.O + (size_t)pair * a.mv_plane;
   short2* Y = a.Y + (size_t)pair * a.mv_plane;
@@ -676,21 +769,18 @@ __global__ void __launch_bounds__(TEAM <= 2 ? 512 : 1024) k_reg_fix(RegArgs a, i
     const uint32_t* lc = lists[cur];
     uint32_t* ln = lists[cur ^ 1];
     uint32_t* next_count = &s_next[cur ^ 1];
-    // one thread per block: whole warps iterate together (the evaluator's early-out is warp-uniform)
-    const uint32_t limit = TEAMSZ == 1 ? ((cnt + 31u) & ~31u) : cnt;
+    const uint32_t limit = (cnt + TPW - 1) / TPW * TPW;  // whole warps iterate together
     for (uint32_t e = team; e < limit; e += nteams) {
       const bool live = e < cnt;
       const int b = (int)lc[live ? e : cnt - 1];
       const int bx = b % a.gw, by = b / a.gw;
       const short2 nv = reg_eval_any<TEAM>(a, pair, O, Y, bx, by, (int)tl, team_mask, live);
-      if (tl == 0 && live && pack_mv(nv) != pack_mv(Y[b])) {
-        Y[b] = nv;
-        for_each_dependent(bx, by, a.gw, a.gh, [&](int d) {
-          if (atomicExch(&stamp[d], ep + 1u) != ep + 1u) ln[atomicAdd(next_count, 1u)] = (uint32_t)d;
-        });
-      }
+      const bool changed = tl == 0 && live && pack_mv(nv) != pack_mv(Y[b]);
+      if (changed) Y[b] = nv;
+      push_dependents(changed, bx, by, a.gw, a.gh, stamp, ep + 1u, ln, next_count);
     }
     __syncthreads();
+    if (a.hist && threadIdx.x == 0) atomicAdd(&a.hist[2 + min(rounds + (uint32_t)r0, 59u)], cnt);
     blocks += cnt;
     cnt = *next_count;
     if (threadIdx.x == 0) s_next[cur] = 0;  // becomes the append counter of the round after next
@@ -700,6 +790,11 @@ __global__ void __launch_bounds__(TEAM <= 2 ? 512 : 1024) k_reg_fix(RegArgs a, i
     __syncthreads();
   }
   if (threadIdx.x == 0) {
+    if (a.hist) {
+      atomicAdd(&a.hist[0], ctr[CTR_COUNT_EVAL]);
+      atomicMax(&a.hist[62], rounds + (uint32_t)r0);
+      atomicAdd(&a.hist[63], rounds);
+    }
     ctr[CTR_COUNT0] = 0;
     ctr[CTR_COUNT1] = 0;
     ctr[CTR_COUNT2] = 0;
@@ -718,8 +813,15 @@ void launch_reg_full(const RegArgs& a, int n, cudaStream_t s) {
   const int team = team_for(a.bs);
   const int lanes = team <= 2 ? 1 : team;
   const size_t nb = (size_t)a.gw * a.gh;
-  k_reg_classify<<<dim3((unsigned)((nb + 255) / 256), n), 256, 0, s>>>(a);
-  dim3 grid((unsigned)((nb * lanes + 127) / 128), n);
+  if ((a.gw & 3) == 0 && (a.mv_plane & 3) == 0) k_reg_classify4<<<dim3((unsigned)((nb / 4 + 255) / 256), n), 256, 0, s>>>(a);
+  else k_reg_classify<<<dim3((unsigned)((nb + 255) / 256), n), 256, 0, s>>>(a);
+  // a fixed-size grid strides over each pair's list (its length is only known on the device): enough CTAs to fill the
+  // chip a few times over, never more than the list could need
+  size_t want = (nb * lanes + 127) / 128;
+  const size_t cap = (size_t)(148 * 16 + n - 1) / n;
+  unsigned gx = (unsigned)(want < cap ? want : cap);
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, n);
   switch (team) {
     case 32: k_reg_eval<32><<<grid, 128, 0, s>>>(a); break;
     case 16: k_reg_eval<16><<<grid, 128, 0, s>>>(a); break;
@@ -747,9 +849,9 @@ void launch_reg_round(const RegArgs& a, int r, int n, cudaStream_t s) {
 
 void launch_reg_fix(const RegArgs& a, int r0, int n, cudaStream_t s) {
   switch (team_for(a.bs)) {
-    case 32: k_reg_fix<32><<<n, 1024, 0, s>>>(a, r0); break;
-    case 16: k_reg_fix<16><<<n, 1024, 0, s>>>(a, r0); break;
-    case 8: k_reg_fix<8><<<n, 1024, 0, s>>>(a, r0); break;
+    case 32: k_reg_fix<32><<<n, 512, 0, s>>>(a, r0); break;
+    case 16: k_reg_fix<16><<<n, 512, 0, s>>>(a, r0); break;
+    case 8: k_reg_fix<8><<<n, 512, 0, s>>>(a, r0); break;
     case 2: k_reg_fix<2><<<n, 512, 0, s>>>(a, r0); break;
     default: k_reg_fix<1><<<n, 512, 0, s>>>(a, r0); break;
   }

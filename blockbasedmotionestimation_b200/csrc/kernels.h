@@ -26,6 +26,8 @@ struct RegArgs {
   uint32_t* stamp;  // de-duplication stamps, one per block
   size_t wl_plane;
   uint32_t* ctr;    // kCtrWords per pair
+  uint32_t* hist = nullptr;  // optional (BBME_FIX_HIST=1): 64 words per sweep, [0] listed blocks, [2 + r] blocks of round r,
+                             // [62] max rounds over pairs, [63] sum of rounds; all summed over the chunk's pairs
 };
 
 // pad (cv::copyMakeBorder constant 0) both frames of n pairs into level 0
