@@ -491,19 +491,33 @@ __device__ __forceinline__ short2 reg_eval_team(const RegArgs& a, int pair, cons
     }
   }
 
-  // smoothness: S_i = sum over gathered candidates k of |c_k.x - c_i.x| + |c_k.y - c_i.y|  (:637-641); computed while
-  // the window loads are in flight
-  int S[9];
+  // smoothness: S_i = sum over gathered candidates k of |c_k.x - c_i.x| + |c_k.y - c_i.y|  (:637-641), computed while the
+  // window loads are in flight.  Accumulated in float like the reference (integer-valued, < 2^24, exact): FADD with |.|
+  // source modifiers runs on the FMA pipe, which is idle here, while the integer form loaded the ALU pipe that the SADs,
+  // funnel shifts and shuffles need.  All nine slots are summed, then the missing slots' share is removed (each holds a
+  // copy of C, i.e. contributes d(i, 0)).
+  float fx[9], fy[9], S[9];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) S[i] = 0;
+  for (int i = 0; i < 9; ++i) {
+    fx[i] = (float)c[i].x;
+    fy[i] = (float)c[i].y;
+    S[i] = 0.f;
+  }
 #pragma unroll
   for (int i = 0; i < 9; ++i) {
 #pragma unroll
     for (int k = i + 1; k < 9; ++k) {
-      const int d = abs((int)c[i].x - (int)c[k].x) + abs((int)c[i].y - (int)c[k].y);
-      const bool both = ((vmask >> i) & (vmask >> k) & 1u) != 0u;
-      S[i] += both ? d : 0;
-      S[k] += both ? d : 0;
+      const float d = __fadd_rn(fabsf(__fsub_rn(fx[i], fx[k])), fabsf(__fsub_rn(fy[i], fy[k])));
+      S[i] = __fadd_rn(S[i], d);
+      S[k] = __fadd_rn(S[k], d);
+    }
+  }
+  {
+    const float n_missing = (float)(9 - __popc(vmask));
+#pragma unroll
+    for (int i = 1; i < 9; ++i) {
+      const float d0 = __fadd_rn(fabsf(__fsub_rn(fx[i], fx[0])), fabsf(__fsub_rn(fy[i], fy[0])));
+      S[i] = __fmaf_rn(-n_missing, d0, S[i]);
     }
   }
 #pragma unroll
@@ -515,7 +529,7 @@ __device__ __forceinline__ short2 reg_eval_team(const RegArgs& a, int pair, cons
   int best_i = 0;
 #pragma unroll
   for (int i = 0; i < 9; ++i) {
-    const float e = ((inb >> i) & 1u) ? __fadd_rn(__uint2float_rn(sad[i]), __fmul_rn(a.lm, __int2float_rn(S[i]))) : FLT_MAX;
+    const float e = ((inb >> i) & 1u) ? __fadd_rn(__uint2float_rn(sad[i]), __fmul_rn(a.lm, S[i])) : FLT_MAX;
     if (i == 0) {
       best = e;
     } else {
@@ -669,7 +683,7 @@ __global__ void __launch_bounds__(256) k_reg_classify(RegArgs a) {
 }
 
 template <int TEAM>
-__global__ void __launch_bounds__(128, TEAM <= 2 ? 4 : 2) k_reg_eval(RegArgs a) {
+__global__ void __launch_bounds__(128, TEAM <= 2 ? 4 : 3) k_reg_eval(RegArgs a) {
   constexpr int TEAMSZ = TEAM <= 2 ? 1 : TEAM;
   constexpr int TPW = 32 / TEAMSZ;  // teams per warp
   const int pair = blockIdx.y;

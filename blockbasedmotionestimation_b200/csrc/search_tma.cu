@@ -66,6 +66,7 @@ struct StageMeta {
   int band;
   int bslot;
   int gblk;        // global block index (pair * blocks + block)
+  int unit;        // the CTA-local unit staged here (consumers check it: see wait_unit)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -79,9 +80,22 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Waits are watched: a barrier that does not complete within ~2^24 polls (seconds; a healthy wait takes microseconds)
+// traps, so a protocol error surfaces as a CUDA error instead of a hung process.  Build with -DBBME_DEBUG_HANG to have
+// the stuck wait print where it is (the printf costs the kernel a stack frame, hence not in the normal build).
+__device__ __forceinline__ void mbar_stuck(int who, int k, uint32_t parity) {
+#ifdef BBME_DEBUG_HANG
+  printf("bbme search kernel: barrier wait stuck (cta %d warp %d who %d unit %d parity %u)\n", (int)blockIdx.x,
+         (int)(threadIdx.x >> 5), who, k, parity);
+#else
+  (void)who; (void)k; (void)parity;
+#endif
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int who = 0, int k = 0) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok = 0;
+  uint32_t polls = 0;
   while (!ok) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -90,6 +104,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(addr), "r"(parity)
         : "memory");
+    if (!ok && ++polls > (1u << 24)) mbar_stuck(who, k, parity);
   }
 }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
@@ -130,6 +145,7 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
   __shared__ uint32_t s_bkey[kBlockSlots];
   __shared__ unsigned long long s_bkey64[kBlockSlots];
   __shared__ uint32_t s_bdone[kBlockSlots];
+  __shared__ uint32_t s_bbusy[kBlockSlots];
   __shared__ uint32_t s_next;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -144,11 +160,13 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], 1);
       s_sdone[i] = 0;
+      s_meta[i].unit = -1;  // shared memory keeps the previous CTA's values: a stale unit number must not match
     }
     for (int i = 0; i < kBlockSlots; ++i) {
       s_bkey[i] = 0xffffffffu;
       s_bkey64[i] = ~0ull;
       s_bdone[i] = 0;
+      s_bbusy[i] = 0;
     }
     s_next = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -170,8 +188,16 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
     if (lane == 0) {
       for (int k = 0; k < my_units; ++k) {
         const int stage = k % kStages;
-        if (k >= kStages) mbar_wait(&s_empty[stage], (uint32_t)((k / kStages) - 1) & 1u);
+        if (k >= kStages) mbar_wait(&s_empty[stage], (uint32_t)((k / kStages) - 1) & 1u, 1, k);
         const int lb = k / a.nbands, band = k - lb * a.nbands;
+        if (band == 0) {
+          // units complete out of order, so the block that used this key slot kBlockSlots blocks ago may still be in
+          // flight (all its units are already staged, so it will finish without this producer)
+          volatile uint32_t* busy = &s_bbusy[lb % kBlockSlots];
+          for (uint32_t polls = 0; *busy != 0u; __nanosleep(32))
+            if (++polls > (1u << 24)) mbar_stuck(2, k, 0);
+          *busy = 1u;
+        }
         const int gblk = cta + lb * G;
         const int pair = gblk / nblocks, b = gblk - pair * nblocks;
         const int by = b / a.gw, bx = b - by * a.gw;
@@ -182,7 +208,7 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
         const int wx_al = wx & ~15;  // floor to a multiple of 16 (two's complement, also for negative wx)
         StageMeta m;
         m.x2 = x2; m.y2 = y2; m.off = wx - wx_al; m.predx = pred.x; m.predy = pred.y;
-        m.valid = valid; m.band = band; m.bslot = lb % kBlockSlots; m.gblk = gblk;
+        m.valid = valid; m.band = band; m.bslot = lb % kBlockSlots; m.gblk = gblk; m.unit = k;
         s_meta[stage] = m;
         if (valid) {
           uint8_t* st = smem + (size_t)stage * a.stage_bytes;
@@ -220,6 +246,8 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
         s_bkey[m.bslot] = 0xffffffffu;
       }
       s_bdone[m.bslot] = 0;
+      __threadfence_block();
+      *reinterpret_cast<volatile uint32_t*>(&s_bbusy[m.bslot]) = 0u;
       const int pair = m.gblk / nblocks, b = m.gblk - pair * nblocks;
       short2 out = make_short2(0, 0);
       if (m.valid) {
@@ -239,6 +267,22 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
     mbar_arrive(&s_empty[stage]);
   };
 
+  // Items are handed out in order but finish out of order, so a warp can hold an item of a unit that is one or more
+  // ring turns ahead of the unit its stage holds (with small search ranges every item is a unit of its own, and eight
+  // warps take eight units of a three-stage ring at once).  A parity wait alone then passes on an older phase of the
+  // same parity -- on a fresh barrier even on the "phase before the first".  The unit number in the stage's metadata
+  // (written by the producer before it arms the barrier, hence visible once the barrier completes; -1 at start) tells
+  // the turns apart.
+  auto wait_unit = [&](int k) {
+    const int st = k % kStages;
+    const uint32_t par = (uint32_t)(k / kStages) & 1u;
+    for (uint32_t polls = 0;; __nanosleep(64)) {
+      mbar_wait(&s_full[st], par, 3, k);
+      if (*reinterpret_cast<volatile int*>(&s_meta[st].unit) == k) break;
+      if (++polls > (1u << 24)) mbar_stuck(4, k, par);
+    }
+  };
+
   for (;;) {
     uint32_t t = 0;
     if (lane == 0) t = atomicAdd(&s_next, 1u);
@@ -248,8 +292,8 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
     const int k0 = T0 / IU;                              // unit of lane 0
     const int split = (k0 + 1) * IU - T0;                // lanes [0, split) belong to k0, the rest to k0 + 1
     const int k1 = (split < 32 && k0 + 1 < my_units) ? k0 + 1 : k0;
-    mbar_wait(&s_full[k0 % kStages], (uint32_t)(k0 / kStages) & 1u);
-    if (k1 != k0) mbar_wait(&s_full[k1 % kStages], (uint32_t)(k1 / kStages) & 1u);
+    wait_unit(k0);
+    if (k1 != k0) wait_unit(k1);
 
     const int T = T0 + lane;
     const bool second = lane >= split;

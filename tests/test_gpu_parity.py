@@ -57,6 +57,16 @@ def test_search_tma_matches_oracle(gpu, oracle, bs, ss, pred_mode):
     assert st["search_kernel_used"] == 2  # TMA kernel ran
 
 
+@pytest.mark.parametrize("bs,ss,h,w", [(16, 48, 512, 768), (32, 64, 768, 1024), (8, 24, 256, 384), (16, 18, 512, 640), (8, 10, 320, 512)])
+@pytest.mark.parametrize("pred_mode", ["small", "wild"])
+def test_search_tma_many_units_per_cta(gpu, oracle, bs, ss, h, w, pred_mode):
+    """More blocks than CTAs: every CTA stages several units through its ring, units complete out of order, and (with
+    predictions that leave the image) work items differ a lot in cost -- the conditions under which a ring turn or a
+    key slot could be confused with an older one."""
+    st = _search_case(gpu, oracle, h, w, bs, ss, 2, 900 + bs + ss, pred_mode=pred_mode)
+    assert st["search_kernel_used"] == 2
+
+
 @pytest.mark.parametrize("bs,ss,h,w", [(16, 272, 160, 224),   # +-128: two TMA boxes, 64-bit key (BASELINE config 5 geometry)
                                       (16, 272, 448, 512),
                                       (32, 160, 256, 320),   # 32x32, +-64: rank space beyond the 14-bit key
