@@ -57,6 +57,9 @@ SIGNATURES = {
     "bbme_estimate": (_I, [_P, _P, _P, _SZ, _P]),
     "bbme_estimate_batch": (_I, [_P, _I, C.POINTER(_P), C.POINTER(_P), _SZ, C.POINTER(_P)]),
     "bbme_estimate_batch_async": (_I, [_P, _I, C.POINTER(_P), C.POINTER(_P), _SZ, C.POINTER(_P)]),
+    "bbme_estimate_upsampled": (_I, [_P, _I, _I, C.POINTER(_P), C.POINTER(_P), _SZ, C.POINTER(_P)]),
+    "bbme_estimate_upsampled_async": (_I, [_P, _I, _I, C.POINTER(_P), C.POINTER(_P), _SZ, C.POINTER(_P)]),
+    "bbme_estimate_upsampled_device": (_I, [_P, _I, _I, _P, _P, _SZ, _SZ, _P, _SZ]),
     "bbme_estimate_device": (_I, [_P, _I, _P, _P, _SZ, _SZ, _P, _SZ]),
     "bbme_estimate_device_compact": (_I, [_P, _I, _P, _P, _SZ, _SZ, _P, _SZ]),
     "bbme_estimate_device_both": (_I, [_P, _I, _P, _P, _SZ, _SZ, _P, _SZ, _P, _SZ]),
@@ -70,6 +73,7 @@ SIGNATURES = {
     "bbme_debug_level_image": (_I, [_P, _I, _I, _I, _P]),
     "bbme_debug_level_mv": (_I, [_P, _I, _I, _I, _P]),
     "bbme_stage_pyrdown": (_I, [_P, _P, _I, _I, _P]),
+    "bbme_stage_resize": (_I, [_P, _P, _I, _I, _I, _P]),
     "bbme_stage_search": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _I, C.POINTER(BbmeStats)]),
     "bbme_stage_regularize": (_I, [_P, _P, _P, _I, _I, _I, C.c_float, _I, _P, C.POINTER(C.c_uint32)]),
     "bbme_stage_divide": (_I, [_P, _P, _I, _I, _P]),

@@ -162,6 +162,43 @@ class Estimator:
         _check(self._lib, self._ctx, self._lib.bbme_estimate_batch(self._ctx, n, p1, p2, pitch, po), "bbme_estimate_batch")
         return out_list
 
+    # -- main()'s quarter-pel wrapper on the device (main_class.cpp:32-33, 58-70)
+    def estimate_upsampled(self, im1_list, im2_list, factor=4):
+        """Frames of (height / factor) x (width / factor) -- width, height as planned -- are up-sampled with
+        cv::resize(INTER_LINEAR) arithmetic, run through the path, and come back as main()'s `subpix_MVs`: padding
+        stripped, every factor-th pixel, vectors / factor.  Returns a list of (h, w, 2) float32 arrays."""
+        single = isinstance(im1_list, np.ndarray) and im1_list.ndim == 2
+        if single:
+            im1_list, im2_list = [im1_list], [im2_list]
+        n = len(im1_list)
+        if n == 0 or n != len(im2_list):
+            raise BbmeError(-1, "estimate_upsampled needs equally many (and at least one) first and second frames")
+        factor = int(factor)
+        if factor < 2 or self.shape["width"] % factor or self.shape["height"] % factor:
+            raise BbmeError(-1, f"factor {factor} does not divide the planned size")
+        h, w = self.shape["height"] // factor, self.shape["width"] // factor
+        PA = C.c_void_p * n
+        p1, p2, po = PA(), PA(), PA()
+        outs = [np.empty((h, w, 2), np.float32) for _ in range(n)]
+        keep = []
+        for i in range(n):
+            a = np.ascontiguousarray(im1_list[i])
+            b = np.ascontiguousarray(im2_list[i])
+            for img in (a, b):
+                if img.dtype != np.uint8 or img.shape != (h, w):
+                    raise BbmeError(-1, f"frames must be uint8 {h}x{w} (planned size / factor)")
+            keep += [a, b]
+            p1[i], p2[i], po[i] = a.ctypes.data, b.ctypes.data, outs[i].ctypes.data
+        _check(self._lib, self._ctx, self._lib.bbme_estimate_upsampled(self._ctx, n, factor, p1, p2, w, po),
+               "bbme_estimate_upsampled")
+        return outs[0] if single else outs
+
+    def estimate_upsampled_device(self, n, factor, d_im1, d_im2, pitch, plane, d_flow, flow_plane):
+        _check(self._lib, self._ctx,
+               self._lib.bbme_estimate_upsampled_device(self._ctx, int(n), int(factor), C.c_void_p(d_im1), C.c_void_p(d_im2),
+                                                        int(pitch), int(plane), C.c_void_p(d_flow), int(flow_plane)),
+               "bbme_estimate_upsampled_device")
+
     # -- device-resident API (raw device pointers, e.g. torch tensors' data_ptr())
     def estimate_device(self, n, d_im1, d_im2, pitch, plane, d_flow, flow_plane):
         _check(self._lib, self._ctx,
@@ -219,6 +256,14 @@ class Estimator:
         h, w = src.shape
         dst = np.empty((h // 2, w // 2), np.uint8)
         _check(self._lib, self._ctx, self._lib.bbme_stage_pyrdown(self._ctx, src.ctypes.data, w, h, dst.ctypes.data), "stage_pyrdown")
+        return dst
+
+    def stage_resize(self, src, factor):
+        src = np.ascontiguousarray(src, np.uint8)
+        h, w = src.shape
+        dst = np.empty((h * factor, w * factor), np.uint8)
+        _check(self._lib, self._ctx, self._lib.bbme_stage_resize(self._ctx, src.ctypes.data, w, h, int(factor), dst.ctypes.data),
+               "bbme_stage_resize")
         return dst
 
     def stage_search(self, im1, im2, block_size, search_size, pred=None, kernel=0):

@@ -197,8 +197,11 @@ void fold_events(bbme_ctx* c, Slot& s) {
 }
 
 // The device pipeline for n pairs resident in slot `s` input planes (d_in1/d_in2), enqueued on s.stream.
+// factor > 1: main()'s quarter-pel wrapper (main_class.cpp:32-33,58-70) -- the frames are (width / factor) x (height /
+// factor) and are up-sampled on the way in; d_flow then receives the stripped, sub-sampled, divided field.
 int run_chunk(bbme_ctx* c, Slot& s, int n, const uint8_t* d_in1, const uint8_t* d_in2, size_t in_pitch,
-              size_t in_plane, float* d_flow, size_t flow_plane, int16_t* d_compact, size_t compact_plane) {
+              size_t in_plane, float* d_flow, size_t flow_plane, int16_t* d_compact, size_t compact_plane,
+              int factor = 1) {
   const bbme_shape& sh = c->shape;
   const int L = sh.num_levels;
   cudaStream_t st = s.stream;
@@ -206,8 +209,15 @@ int run_chunk(bbme_ctx* c, Slot& s, int n, const uint8_t* d_in1, const uint8_t* 
   s.last_n = n > s.last_n ? n : s.last_n;
   mark(c, s, TAG_BEGIN);
   // ---- MF::MF: pad + Gaussian pyramid (motion_framework.cpp:57-106)
-  launch_pad(d_in1, d_in2, in_pitch, in_plane, sh.width, sh.height, sh.padding_x, sh.padding_y, s.img[0][0],
-             s.img[1][0], c->pitch[0], c->plane[0], sh.padded_width, sh.padded_height, n, st);
+  if (factor > 1) {
+    ResizeTaps taps;
+    if (make_resize_taps(factor, &taps) != 0) return fail(c, BBME_E_ARG, "up-sampling factor %d (supported: 2, 4, 8)", factor);
+    launch_resize_pad(d_in1, d_in2, in_pitch, in_plane, sh.width / factor, sh.height / factor, taps, sh.padding_x,
+                      sh.padding_y, s.img[0][0], s.img[1][0], c->pitch[0], c->plane[0], sh.padded_height, n, st);
+  } else {
+    launch_pad(d_in1, d_in2, in_pitch, in_plane, sh.width, sh.height, sh.padding_x, sh.padding_y, s.img[0][0],
+               s.img[1][0], c->pitch[0], c->plane[0], sh.padded_width, sh.padded_height, n, st);
+  }
   ++c->launches;
   for (int l = 1; l < L; ++l) {
     ImgView a{s.img[0][l - 1], sh.level_width[l - 1], sh.level_height[l - 1], c->pitch[l - 1], c->plane[l - 1]};
@@ -290,7 +300,11 @@ int run_chunk(bbme_ctx* c, Slot& s, int n, const uint8_t* d_in1, const uint8_t* 
     mark(c, s, TAG_REG);
   }
   // ---- final dense field (motion_framework.cpp:205-206,218)
-  if (d_flow) {
+  if (d_flow && factor > 1) {
+    launch_export_subsample(s.mv_final[0], sh.padded_width / 2, c->cap[0], sh.padding_x, sh.padding_y, factor, d_flow,
+                            sh.width / factor, sh.height / factor, flow_plane, n, st);
+    ++c->launches;
+  } else if (d_flow) {
     launch_export(s.mv_final[0], sh.padded_width / 2, c->cap[0], d_flow, sh.padded_width, sh.padded_height, flow_plane, n, st);
     ++c->launches;
   }
@@ -554,34 +568,60 @@ int bbme_get_stats(bbme_ctx* c, bbme_stats* out) {
   return BBME_OK;
 }
 
-int bbme_estimate_batch_async(bbme_ctx* c, int n, const uint8_t* const* im1, const uint8_t* const* im2, size_t pitch,
-                              float* const* flow) {
+static int estimate_batch_async_impl(bbme_ctx* c, int n, int factor, const uint8_t* const* im1, const uint8_t* const* im2,
+                                     size_t pitch, float* const* flow) {
   if (!c) return BBME_E_ARG;
   if (!c->planned) return fail(c, BBME_E_STATE, "bbme_estimate_batch before bbme_plan");
-  if (n <= 0 || !im1 || !im2 || !flow || pitch < (size_t)c->shape.width) return fail(c, BBME_E_ARG, "bbme_estimate_batch: bad arguments");
+  if (factor < 1 || c->shape.width % factor || c->shape.height % factor)
+    return fail(c, BBME_E_ARG, "up-sampling factor %d does not divide the planned size %dx%d", factor, c->shape.width, c->shape.height);
+  const int w = c->shape.width / factor, h = c->shape.height / factor;  // size of the frames handed in
+  if (n <= 0 || !im1 || !im2 || !flow || pitch < (size_t)w) return fail(c, BBME_E_ARG, "bbme_estimate_batch: bad arguments");
   for (int i = 0; i < n; ++i)
     if (!im1[i] || !im2[i] || !flow[i]) return fail(c, BBME_E_ARG, "bbme_estimate_batch: null buffer for pair %d", i);
   CUDA_TRY(c, cudaSetDevice(c->device));
   begin_call(c);
   const int chunk = c->opt.chunk_pairs;
-  const size_t flow_bytes = c->out_plane * sizeof(float);
+  const size_t in_pitch = factor > 1 ? (size_t)round_up(w, 16) : (size_t)c->in_pitch;
+  const size_t in_plane = factor > 1 ? in_pitch * h : c->in_plane;
+  const size_t out_plane = factor > 1 ? (size_t)w * h * 2 : c->out_plane;  // floats per pair
+  const size_t flow_bytes = out_plane * sizeof(float);
   int ci = c->next_slot;
   for (int start = 0; start < n; start += chunk, ++ci) {
     Slot& s = c->slots[ci % c->slots.size()];
     const int m = (n - start < chunk) ? (n - start) : chunk;
     for (int i = 0; i < m; ++i) {
-      CUDA_TRY(c, cudaMemcpy2DAsync(s.in1 + (size_t)i * c->in_plane, c->in_pitch, im1[start + i], pitch, c->shape.width,
-                                    c->shape.height, cudaMemcpyHostToDevice, s.stream));
-      CUDA_TRY(c, cudaMemcpy2DAsync(s.in2 + (size_t)i * c->in_plane, c->in_pitch, im2[start + i], pitch, c->shape.width,
-                                    c->shape.height, cudaMemcpyHostToDevice, s.stream));
+      CUDA_TRY(c, cudaMemcpy2DAsync(s.in1 + (size_t)i * in_plane, in_pitch, im1[start + i], pitch, w, h,
+                                    cudaMemcpyHostToDevice, s.stream));
+      CUDA_TRY(c, cudaMemcpy2DAsync(s.in2 + (size_t)i * in_plane, in_pitch, im2[start + i], pitch, w, h,
+                                    cudaMemcpyHostToDevice, s.stream));
     }
-    int rc = run_chunk(c, s, m, s.in1, s.in2, c->in_pitch, c->in_plane, s.out, c->out_plane, nullptr, 0);
+    int rc = run_chunk(c, s, m, s.in1, s.in2, in_pitch, in_plane, s.out, out_plane, nullptr, 0, factor);
     if (rc) return rc;
     for (int i = 0; i < m; ++i)
-      CUDA_TRY(c, cudaMemcpyAsync(flow[start + i], s.out + (size_t)i * c->out_plane, flow_bytes, cudaMemcpyDeviceToHost, s.stream));
+      CUDA_TRY(c, cudaMemcpyAsync(flow[start + i], s.out + (size_t)i * out_plane, flow_bytes, cudaMemcpyDeviceToHost, s.stream));
   }
   c->next_slot = ci % (int)c->slots.size();
   return BBME_OK;
+}
+
+int bbme_estimate_batch_async(bbme_ctx* c, int n, const uint8_t* const* im1, const uint8_t* const* im2, size_t pitch,
+                              float* const* flow) {
+  return estimate_batch_async_impl(c, n, 1, im1, im2, pitch, flow);
+}
+
+int bbme_estimate_upsampled_async(bbme_ctx* c, int n, int factor, const uint8_t* const* im1, const uint8_t* const* im2,
+                                  size_t pitch, float* const* flow) {
+  if (factor < 2) return c ? fail(c, BBME_E_ARG, "bbme_estimate_upsampled: factor must be 2, 4 or 8") : BBME_E_ARG;
+  return estimate_batch_async_impl(c, n, factor, im1, im2, pitch, flow);
+}
+
+int bbme_estimate_upsampled(bbme_ctx* c, int n, int factor, const uint8_t* const* im1, const uint8_t* const* im2,
+                            size_t pitch, float* const* flow) {
+  int rc = bbme_estimate_upsampled_async(c, n, factor, im1, im2, pitch, flow);
+  if (rc) return rc;
+  rc = sync_all(c);
+  if (rc) return rc;
+  return collect_after_sync(c);
 }
 
 int bbme_estimate_batch(bbme_ctx* c, int n, const uint8_t* const* im1, const uint8_t* const* im2, size_t pitch,
@@ -598,12 +638,16 @@ int bbme_estimate(bbme_ctx* c, const uint8_t* im1, const uint8_t* im2, size_t pi
 }
 
 static int estimate_device_impl(bbme_ctx* c, int n, const uint8_t* d1, const uint8_t* d2, size_t pitch, size_t plane,
-                                float* d_flow, size_t flow_plane, int16_t* d_mv, size_t mv_plane) {
+                                float* d_flow, size_t flow_plane, int16_t* d_mv, size_t mv_plane, int factor = 1) {
   if (!c) return BBME_E_ARG;
   if (!c->planned) return fail(c, BBME_E_STATE, "bbme_estimate_device before bbme_plan");
-  if (n <= 0 || !d1 || !d2 || pitch < (size_t)c->shape.width || plane < pitch * (size_t)c->shape.height)
+  if (factor < 1 || c->shape.width % factor || c->shape.height % factor)
+    return fail(c, BBME_E_ARG, "up-sampling factor %d does not divide the planned size %dx%d", factor, c->shape.width, c->shape.height);
+  const size_t fw = (size_t)(c->shape.width / factor), fh = (size_t)(c->shape.height / factor);
+  if (n <= 0 || !d1 || !d2 || pitch < fw || plane < pitch * fh)
     return fail(c, BBME_E_ARG, "bbme_estimate_device: bad arguments");
-  if (d_flow && flow_plane < c->out_plane) return fail(c, BBME_E_ARG, "bbme_estimate_device: flow plane stride too small");
+  if (d_flow && flow_plane < (factor > 1 ? fw * fh * 2 : c->out_plane))
+    return fail(c, BBME_E_ARG, "bbme_estimate_device: flow plane stride too small");
   if (d_mv && mv_plane < c->cap[0] * 2) return fail(c, BBME_E_ARG, "bbme_estimate_device: mv plane stride too small");
   CUDA_TRY(c, cudaSetDevice(c->device));
   begin_call(c);
@@ -614,7 +658,7 @@ static int estimate_device_impl(bbme_ctx* c, int n, const uint8_t* d1, const uin
     const int m = (n - start < chunk) ? (n - start) : chunk;
     int rc = run_chunk(c, s, m, d1 + (size_t)start * plane, d2 + (size_t)start * plane, pitch, plane,
                        d_flow ? d_flow + (size_t)start * flow_plane : nullptr, flow_plane,
-                       d_mv ? d_mv + (size_t)start * mv_plane : nullptr, mv_plane);
+                       d_mv ? d_mv + (size_t)start * mv_plane : nullptr, mv_plane, factor);
     if (rc) return rc;
   }
   return BBME_OK;
@@ -624,6 +668,12 @@ int bbme_estimate_device(bbme_ctx* c, int n, const uint8_t* d1, const uint8_t* d
                          float* d_flow, size_t flow_plane) {
   if (!d_flow) return c ? fail(c, BBME_E_ARG, "bbme_estimate_device: null flow") : BBME_E_ARG;
   return estimate_device_impl(c, n, d1, d2, pitch, plane, d_flow, flow_plane, nullptr, 0);
+}
+
+int bbme_estimate_upsampled_device(bbme_ctx* c, int n, int factor, const uint8_t* d1, const uint8_t* d2, size_t pitch,
+                                   size_t plane, float* d_flow, size_t flow_plane) {
+  if (!d_flow || factor < 2) return c ? fail(c, BBME_E_ARG, "bbme_estimate_upsampled_device: null flow or factor < 2") : BBME_E_ARG;
+  return estimate_device_impl(c, n, d1, d2, pitch, plane, d_flow, flow_plane, nullptr, 0, factor);
 }
 
 int bbme_estimate_device_compact(bbme_ctx* c, int n, const uint8_t* d1, const uint8_t* d2, size_t pitch, size_t plane,
@@ -729,6 +779,24 @@ int bbme_stage_pyrdown(bbme_ctx* c, const uint8_t* src, int w, int h, uint8_t* d
   if (!dd) return fail(c, BBME_E_NOMEM, "stage: cudaMalloc failed");
   ImgView v{ds, w, h, sp, (size_t)sp * h};
   launch_pyrdown(v, v, dd, dd + (size_t)dp * dh, dp, 0, 1, 0);
+  CUDA_TRY(c, cudaDeviceSynchronize());
+  CUDA_TRY(c, cudaMemcpy2D(dst, dw, dd, dp, dw, dh, cudaMemcpyDeviceToHost));
+  return BBME_OK;
+}
+
+int bbme_stage_resize(bbme_ctx* c, const uint8_t* src, int w, int h, int factor, uint8_t* dst) {
+  if (!c || !src || !dst || w < 1 || h < 1) return BBME_E_ARG;
+  ResizeTaps taps;
+  if (make_resize_taps(factor, &taps) != 0) return fail(c, BBME_E_ARG, "bbme_stage_resize: factor %d (supported: 2, 4, 8)", factor);
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  Scratch sc;
+  const int sp = round_up(w, 16);
+  uint8_t* ds = sc.get<uint8_t>((size_t)sp * h, true);
+  const int dw = w * factor, dh = h * factor, dp = round_up(dw + 4, 64);
+  uint8_t* dd = sc.get<uint8_t>((size_t)dp * dh * 2, true);
+  if (!ds || !dd) return fail(c, BBME_E_NOMEM, "stage: cudaMalloc failed");
+  CUDA_TRY(c, cudaMemcpy2D(ds, sp, src, w, w, h, cudaMemcpyHostToDevice));
+  launch_resize_pad(ds, ds, sp, 0, w, h, taps, 0, 0, dd, dd + (size_t)dp * dh, dp, 0, dh, 1, 0);
   CUDA_TRY(c, cudaDeviceSynchronize());
   CUDA_TRY(c, cudaMemcpy2D(dst, dw, dd, dp, dw, dh, cudaMemcpyDeviceToHost));
   return BBME_OK;

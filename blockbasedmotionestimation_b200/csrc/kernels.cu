@@ -6,6 +6,7 @@
 #include "kernels.h"
 
 #include <float.h>
+#include <math.h>
 
 namespace bbme {
 
@@ -51,6 +52,79 @@ void launch_pad(const uint8_t* in1, const uint8_t* in2, size_t in_pitch, size_t 
   dim3 block(128);
   dim3 grid((out_pitch / 16 + block.x - 1) / block.x, ph, 2 * n);
   k_pad<<<grid, block, 0, s>>>(in1, in2, in_pitch, in_plane, w, h, pad_x, pad_y, out1, out2, out_pitch, out_plane, ph);
+}
+
+// ============================================================================================ resize + pad
+// main()'s quarter-pel wrapper (main_class.cpp:32-33): cv::resize(img, img, Size(), f, f, INTER_LINEAR) on 8-bit frames,
+// fused with the copyMakeBorder of MF::MF (motion_framework.cpp:60-61): the up-sampled frame is never stored unpadded.
+// OpenCV's fixed-point algorithm (pinned against cv2 by tests/golden/resize_cv2.npz): 11-bit tap weights,
+// horizontal pass in int32, vertical pass (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2; x taps that
+// fall outside move inside and lose their weight, y taps are clamped by row index.  For the power-of-two factors
+// supported here the tap position of destination index d = q * f + p is exactly q + off[p] with weight wt[p].
+__global__ void __launch_bounds__(128) k_resize_pad(const uint8_t* __restrict__ in1, const uint8_t* __restrict__ in2,
+                                                    size_t in_pitch, size_t in_plane, int w, int h, ResizeTaps taps,
+                                                    int pad_x, int pad_y, uint8_t* __restrict__ out1,
+                                                    uint8_t* __restrict__ out2, int out_pitch, size_t out_plane, int ph) {
+  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  const int y = blockIdx.y;
+  const int pair = blockIdx.z >> 1;
+  const int frame = blockIdx.z & 1;
+  if (x0 >= out_pitch || y >= ph) return;
+  const uint8_t* in = (frame ? in2 : in1) + (size_t)pair * in_plane;
+  uint8_t* out = (frame ? out2 : out1) + (size_t)pair * out_plane + (size_t)y * out_pitch + x0;
+  const int f = taps.factor, sh = taps.shift;
+  const int dy = y - pad_y;
+  uint32_t wd[4] = {0u, 0u, 0u, 0u};
+  if (dy >= 0 && dy < h * f) {
+    const int py = dy & (f - 1);
+    const int sy = (dy >> sh) + taps.off[py];
+    const int b1 = taps.wt[py], b0 = 2048 - b1;
+    const uint8_t* r0 = in + (size_t)min(max(sy, 0), h - 1) * in_pitch;
+    const uint8_t* r1 = in + (size_t)min(max(sy + 1, 0), h - 1) * in_pitch;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int dx = x0 + i - pad_x;
+      if (dx < 0 || dx >= w * f) continue;
+      const int px = dx & (f - 1);
+      int sx = (dx >> sh) + taps.off[px];
+      int a1 = taps.wt[px];
+      if (sx < 0) { sx = 0; a1 = 0; }
+      if (sx >= w - 1) { sx = w - 1; a1 = 0; }
+      const int a0 = 2048 - a1;
+      const int sx1 = min(sx + 1, w - 1);
+      const int h0 = (int)__ldg(r0 + sx) * a0 + (int)__ldg(r0 + sx1) * a1;
+      const int h1 = (int)__ldg(r1 + sx) * a0 + (int)__ldg(r1 + sx1) * a1;
+      const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      wd[i >> 2] |= (uint32_t)v << ((i & 3) * 8);
+    }
+  }
+  *reinterpret_cast<uint4*>(out) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+}
+
+int make_resize_taps(int factor, ResizeTaps* t) {
+  if (!(factor == 2 || factor == 4 || factor == 8)) return -1;
+  t->factor = factor;
+  t->shift = factor == 2 ? 1 : (factor == 4 ? 2 : 3);
+  for (int p = 0; p < 8; ++p) { t->off[p] = 0; t->wt[p] = 0; }
+  const double scale = 1.0 / (double)factor;
+  for (int p = 0; p < factor; ++p) {
+    // OpenCV: fx = (float)((dx + 0.5) * scale_x - 0.5); sx = cvFloor(fx); fx -= sx; weight = cvRound(fx * 2048)
+    float fx = (float)(((double)p + 0.5) * scale - 0.5);
+    const int sx = (int)floorf(fx);
+    fx -= (float)sx;
+    t->off[p] = sx;
+    t->wt[p] = (int)lrintf(fx * 2048.f);
+  }
+  return 0;
+}
+
+void launch_resize_pad(const uint8_t* in1, const uint8_t* in2, size_t in_pitch, size_t in_plane, int w, int h,
+                       const ResizeTaps& taps, int pad_x, int pad_y, uint8_t* out1, uint8_t* out2, int out_pitch,
+                       size_t out_plane, int ph, int n, cudaStream_t s) {
+  dim3 block(128);
+  dim3 grid((out_pitch / 16 + block.x - 1) / block.x, ph, 2 * n);
+  k_resize_pad<<<grid, block, 0, s>>>(in1, in2, in_pitch, in_plane, w, h, taps, pad_x, pad_y, out1, out2, out_pitch,
+                                      out_plane, ph);
 }
 
 // ============================================================================================ pyrDown
@@ -280,6 +354,28 @@ void launch_export_compact(const short2* mv2, int gw2, int gh2, size_t mv_plane,
                            cudaStream_t s) {
   dim3 grid((gw2 * gh2 + 255) / 256, n);
   k_export_compact<<<grid, 256, 0, s>>>(mv2, gw2 * gh2, mv_plane, out, out_plane);
+}
+
+// main()'s post-processing (main_class.cpp:58-70) on the device: strip the padding, keep every factor-th pixel, divide
+// the vectors by the factor -> (height / factor) x (width / factor) x 2 floats.  The dense padded field is never built.
+__global__ void __launch_bounds__(256) k_export_subsample(const short2* __restrict__ mv2, int gw2, size_t mv_plane,
+                                                          int pad_x, int pad_y, int factor, float* __restrict__ out,
+                                                          int ow, int oh, size_t out_plane) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int pair = blockIdx.z;
+  if (x >= ow || y >= oh) return;
+  const int sx = pad_x + x * factor, sy = pad_y + y * factor;  // pixel (i, j) of the padded field, :62-68
+  const short2 m = __ldg(&mv2[(size_t)pair * mv_plane + (size_t)(sy >> 1) * gw2 + (sx >> 1)]);
+  const float inv = (float)factor;
+  reinterpret_cast<float2*>(out + (size_t)pair * out_plane)[(size_t)y * ow + x] =
+      make_float2(__fdiv_rn((float)m.x, inv), __fdiv_rn((float)m.y, inv));
+}
+
+void launch_export_subsample(const short2* mv2, int gw2, size_t mv_plane, int pad_x, int pad_y, int factor, float* out,
+                             int ow, int oh, size_t out_plane, int n, cudaStream_t s) {
+  dim3 grid((ow + 255) / 256, oh, n);
+  k_export_subsample<<<grid, 256, 0, s>>>(mv2, gw2, mv_plane, pad_x, pad_y, factor, out, ow, oh, out_plane);
 }
 
 // ============================================================================================ regularisation

@@ -34,6 +34,19 @@ struct RegArgs {
 void launch_pad(const uint8_t* in1, const uint8_t* in2, size_t in_pitch, size_t in_plane, int w, int h, int pad_x,
                 int pad_y, uint8_t* out1, uint8_t* out2, int out_pitch, size_t out_plane, int pw, int ph, int n,
                 cudaStream_t s);
+// cv::resize(INTER_LINEAR) by a power-of-two factor fused with the pad (main()'s quarter-pel wrapper, main_class.cpp:32-33)
+struct ResizeTaps {
+  int factor, shift;
+  int off[8];  // tap position of destination phase p relative to d / factor
+  int wt[8];   // 11-bit weight of the second tap
+};
+int make_resize_taps(int factor, ResizeTaps* t);  // 0 on success; factor must be 2, 4 or 8
+void launch_resize_pad(const uint8_t* in1, const uint8_t* in2, size_t in_pitch, size_t in_plane, int w, int h,
+                       const ResizeTaps& taps, int pad_x, int pad_y, uint8_t* out1, uint8_t* out2, int out_pitch,
+                       size_t out_plane, int ph, int n, cudaStream_t s);
+// main()'s strip + sub-sample + divide (main_class.cpp:58-70) from the 2x2-granular level-0 field
+void launch_export_subsample(const short2* mv2, int gw2, size_t mv_plane, int pad_x, int pad_y, int factor, float* out,
+                             int ow, int oh, size_t out_plane, int n, cudaStream_t s);
 // cv::pyrDown to (sw/2, sh/2), both frames of n pairs
 void launch_pyrdown(ImgView src1, ImgView src2, uint8_t* dst1, uint8_t* dst2, int dpitch, size_t dplane, int n,
                     cudaStream_t s);

@@ -27,7 +27,7 @@ extern "C" {
 #endif
 
 #define BBME_MAX_LEVELS 16
-#define BBME_VERSION 100
+#define BBME_VERSION 101
 
 typedef enum {
   BBME_OK = 0,
@@ -117,11 +117,27 @@ int bbme_estimate_batch(bbme_ctx* ctx, int n, const uint8_t* const* im1, const u
 int bbme_estimate_batch_async(bbme_ctx* ctx, int n, const uint8_t* const* im1, const uint8_t* const* im2,
                               size_t pitch_bytes, float* const* flow);
 
+/* main()'s quarter-pel wrapper around the path, on the device (main_class.cpp:32-33 and :58-70): the frames are
+ * (width / factor) x (height / factor) -- width, height as given to bbme_plan, i.e. the size MF sees -- and are up-sampled
+ * with the arithmetic of cv::resize(img, img, Size(), factor, factor, INTER_LINEAR) on the way into level 0; each flow
+ * buffer receives (height / factor) x (width / factor) x 2 floats: the field with its padding stripped, every factor-th
+ * pixel kept and the vectors divided by factor (main's subpix_MVs).  factor: 2, 4 or 8 (main uses 4).  The copies per
+ * pair shrink by factor^2 (input) and by more than that (output), so this path is not bound by the host link. */
+int bbme_estimate_upsampled(bbme_ctx* ctx, int n, int factor, const uint8_t* const* im1, const uint8_t* const* im2,
+                            size_t pitch_bytes, float* const* flow);
+int bbme_estimate_upsampled_async(bbme_ctx* ctx, int n, int factor, const uint8_t* const* im1,
+                                  const uint8_t* const* im2, size_t pitch_bytes, float* const* flow);
+
 /* n <= chunk_pairs pairs already in device memory (same device as the context).  Frames are n planes of
  * `plane_stride` bytes; flow is n planes of flow_plane_stride floats.  Runs on slot 0's stream and returns
  * after enqueueing; call bbme_sync before reading.  This is the "inputs resident in HBM" entry point. */
 int bbme_estimate_device(bbme_ctx* ctx, int n, const uint8_t* d_im1, const uint8_t* d_im2, size_t pitch_bytes,
                          size_t plane_stride, float* d_flow, size_t flow_plane_stride);
+
+/* bbme_estimate_upsampled with frames and result in device memory (frames: (height/factor) rows of (width/factor)
+ * bytes; flow planes of at least (height/factor) * (width/factor) * 2 floats). */
+int bbme_estimate_upsampled_device(bbme_ctx* ctx, int n, int factor, const uint8_t* d_im1, const uint8_t* d_im2,
+                                   size_t pitch_bytes, size_t plane_stride, float* d_flow, size_t flow_plane_stride);
 
 /* Compact result of the same computation: the 2x2-granular int16 field (padded_height/2 x padded_width/2 x 2),
  * i.e. the information content of the dense float field (motion_framework.cpp:205-206 replicates it 2x2). */
@@ -159,6 +175,8 @@ int bbme_debug_level_mv(bbme_ctx* ctx, int pair, int level, int which, int16_t* 
 /* ---- single stages on host buffers (upload, one kernel, download): parity tests against the oracle ---- */
 /* cv::pyrDown(src, Size(w/2, h/2)), motion_framework.cpp:89-90. */
 int bbme_stage_pyrdown(bbme_ctx* ctx, const uint8_t* src, int w, int h, uint8_t* dst);
+/* cv::resize(src, Size(), factor, factor, INTER_LINEAR), main_class.cpp:32-33.  dst: (factor*h) x (factor*w) bytes. */
+int bbme_stage_resize(bbme_ctx* ctx, const uint8_t* src, int w, int h, int factor, uint8_t* dst);
 /* MF::calcLevelBM (motion_framework.cpp:226-244) on one level.  mv: (h/bs) x (w/bs) x 2 int16, holds the
  * prediction on entry and the result on exit.  kernel: as bbme_options.search_kernel. */
 int bbme_stage_search(bbme_ctx* ctx, const uint8_t* im1, const uint8_t* im2, int w, int h, int block_size,

@@ -523,6 +523,66 @@ int orc_estimate_many(int n, const uint8_t* const* im1, const uint8_t* const* im
 
 static const float kFloTag = 202021.25f; /* "PIEH", rw_flow.cpp:25-26 */
 
+/* ------------------------------------------------------------------------------------------------ main()'s wrapper
+ * cv::resize(INTER_LINEAR), 8-bit, integer up-sampling factor (main_class.cpp:32-33).  Restated from OpenCV's
+ * published algorithm (see the header); every step is integer except the tap positions, which OpenCV computes as
+ * float((d + 0.5) * scale - 0.5) with scale = 1 / factor in double. */
+static void resize_taps(int d, int factor, int n_src, int clamp_weight, int* s0, int* s1, int* w0, int* w1) {
+  const double scale = 1.0 / (double)factor;
+  float f = (float)(((double)d + 0.5) * scale - 0.5);
+  int s = (int)floorf(f);
+  f -= (float)s;
+  if (clamp_weight) { /* x direction: out-of-range taps move inside and lose their weight */
+    if (s < 0) { s = 0; f = 0.f; }
+    if (s >= n_src - 1) { s = n_src - 1; f = 0.f; }
+  }
+  *w0 = (int)lrintf((1.f - f) * 2048.f);
+  *w1 = (int)lrintf(f * 2048.f);
+  int a = s, b = s + 1;
+  if (a < 0) a = 0;
+  if (a > n_src - 1) a = n_src - 1;
+  if (b < 0) b = 0;
+  if (b > n_src - 1) b = n_src - 1;
+  *s0 = a;
+  *s1 = b;
+}
+
+void orc_resize_linear(const uint8_t* src, int w, int h, int factor, uint8_t* dst) {
+  const int dw = w * factor, dh = h * factor;
+  int* xs0 = (int*)malloc(sizeof(int) * 4 * (size_t)dw);
+  int *xs1 = xs0 + dw, *xw0 = xs1 + dw, *xw1 = xw0 + dw;
+  for (int x = 0; x < dw; ++x) resize_taps(x, factor, w, 1, &xs0[x], &xs1[x], &xw0[x], &xw1[x]);
+  for (int y = 0; y < dh; ++y) {
+    int y0, y1, b0, b1;
+    resize_taps(y, factor, h, 0, &y0, &y1, &b0, &b1);
+    const uint8_t* r0 = src + (size_t)y0 * w;
+    const uint8_t* r1 = src + (size_t)y1 * w;
+    for (int x = 0; x < dw; ++x) {
+      const int h0 = r0[xs0[x]] * xw0[x] + r0[xs1[x]] * xw1[x];
+      const int h1 = r1[xs0[x]] * xw0[x] + r1[xs1[x]] * xw1[x];
+      int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      if (v < 0) v = 0;
+      if (v > 255) v = 255;
+      dst[(size_t)y * dw + x] = (uint8_t)v;
+    }
+  }
+  free(xs0);
+}
+
+void orc_strip_subsample(const float* padded_flow, int padded_w, int padded_h, int pad_x, int pad_y, int factor,
+                         float* out) {
+  const int ow = (padded_w - 2 * pad_x) / factor;
+  for (int i = pad_y; i < padded_h - pad_y; i += factor) {      /* main_class.cpp:62-70 */
+    for (int j = pad_x; j < padded_w - pad_x; j += factor) {
+      const float* p = padded_flow + ((size_t)i * padded_w + j) * 2;
+      float* q = out + ((size_t)((i - pad_y) / factor) * ow + (j - pad_x) / factor) * 2;
+      q[0] = p[0] / (float)factor;
+      q[1] = p[1] / (float)factor;
+    }
+  }
+}
+
+
 static int flo_open(const char* path, FILE** fp, int* w, int* h) {
   if (!path) return ORC_E_ARG;
   const char* dot = strrchr(path, '.');

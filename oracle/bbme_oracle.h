@@ -101,6 +101,19 @@ int orc_estimate_many(int n, const uint8_t* const* im1, const uint8_t* const* im
                       int levels, const int* search_size, const int* block_size, int sweeps, float* const* flow_out,
                       int threads, orc_stats* st_sum);
 
+/* main()'s quarter-pel wrapper around the path (main_class.cpp:32-33): cv::resize(img, img, Size(), f, f, INTER_LINEAR)
+ * for 8-bit images.  OpenCV is not in the reference tree; this restates its published fixed-point algorithm (imgproc
+ * resize.cpp: 11-bit coefficients cvRound(w * 2048), horizontal pass in int32, vertical pass
+ * (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2; x taps clamped with the weight zeroed, y taps
+ * clamped by row index) and is pinned bit-for-bit against the container's cv2 4.13.0 (tests/golden/resize_cv2.npz).
+ * dst is (factor * w) x (factor * h), dense. */
+void orc_resize_linear(const uint8_t* src, int w, int h, int factor, uint8_t* dst);
+
+/* main_class.cpp:58-70: strip the padding, keep every factor-th pixel, divide the vectors by factor.
+ * out is (h / factor) x (w / factor) x 2 floats with (w, h) the size MF was constructed on. */
+void orc_strip_subsample(const float* padded_flow, int padded_w, int padded_h, int pad_x, int pad_y, int factor,
+                         float* out);
+
 /* Flow::ReadFlowFile / WriteFlowFile / CalculateMSE, rw_flow.cpp:50-136,139-200,309-332. */
 int orc_flo_read_header(const char* path, int* w, int* h);
 int orc_flo_read(const char* path, float* data, int w, int h);

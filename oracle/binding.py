@@ -55,6 +55,8 @@ def load():
         lib.orc_flo_read.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int]
         lib.orc_flo_write.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int]
         lib.orc_aee.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        lib.orc_resize_linear.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        lib.orc_strip_subsample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _lib = lib
     return _lib
 
@@ -198,6 +200,26 @@ def copy_mvs(coarse, coarse_block_size):
     fine = np.zeros((2 * ch, 2 * cw, 2), np.float32)
     lib.orc_copy_mvs(coarse.ctypes.data, cw, ch, coarse_block_size, fine.ctypes.data)
     return fine
+
+
+def resize_linear(src, factor):
+    """cv::resize(src, Size(), factor, factor, INTER_LINEAR) for 8-bit (main_class.cpp:32-33)."""
+    lib = load()
+    src = np.ascontiguousarray(src, np.uint8)
+    h, w = src.shape
+    dst = np.empty((h * factor, w * factor), np.uint8)
+    lib.orc_resize_linear(src.ctypes.data, w, h, int(factor), dst.ctypes.data)
+    return dst
+
+
+def strip_subsample(flow, pad_x, pad_y, factor):
+    """main_class.cpp:58-70: padded dense field -> (h / factor) x (w / factor) x 2 sub-pixel field."""
+    lib = load()
+    flow = np.ascontiguousarray(flow, np.float32)
+    ph, pw = flow.shape[:2]
+    out = np.zeros(((ph - 2 * pad_y) // factor, (pw - 2 * pad_x) // factor, 2), np.float32)
+    lib.orc_strip_subsample(flow.ctypes.data, pw, ph, int(pad_x), int(pad_y), int(factor), out.ctypes.data)
+    return out
 
 
 def flo_read(path):

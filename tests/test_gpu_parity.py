@@ -240,6 +240,44 @@ def test_plan_errors_are_loud():
             est.estimate(np.zeros((96, 64), np.uint8), np.zeros((96, 64), np.uint8))
 
 
+# ------------------------------------------------------------------------------------------ main()'s quarter-pel wrapper
+@pytest.mark.parametrize("shape,factor", [((37, 53), 4), ((33, 47), 2), ((20, 30), 8), ((97, 146), 4), ((2, 3), 4), ((388, 584), 4)])
+def test_resize_matches_oracle(gpu, oracle, shape, factor):
+    """cv::resize(INTER_LINEAR) (main_class.cpp:32-33) on the device == the oracle (which is pinned against cv2)."""
+    src = np.random.default_rng(shape[0] * 31 + factor).integers(0, 256, shape).astype(np.uint8)
+    got = gpu.stage_resize(src, factor)
+    want = oracle.resize_linear(src, factor)
+    assert np.array_equal(got, want), describe_diff(got, want)
+
+
+def test_resize_matches_cv2_golden(gpu):
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "resize_cv2.npz"))
+    for i in range(len([k for k in d.files if k.startswith("in_")])):
+        got = gpu.stage_resize(d[f"in_{i}"], int(d[f"factor_{i}"][0]))
+        assert np.array_equal(got, d[f"out_{i}"]), (i, describe_diff(got, d[f"out_{i}"]))
+
+
+@pytest.mark.parametrize("h,w,factor,ss,bs", [(48, 64, 4, [24, 24], [8, 8]), (45, 61, 4, [48, 48, 48], [16, 16, 16]),
+                                              (90, 120, 2, [16, 16], [8, 8])])
+def test_upsampled_pipeline_matches_oracle(oracle, h, w, factor, ss, bs):
+    """main()'s whole flow on the device (resize -> MF -> strip / sub-sample / divide, main_class.cpp:32-70) == the oracle's
+    resize, estimate and strip_subsample chained; also a batch of two pairs."""
+    f1, f2 = make_pair(h, w, 500 + h, shift=(1, -1), max_patch_shift=2)
+    g1, g2 = make_pair(h, w, 600 + h, shift=(-1, 1), max_patch_shift=1)
+    with bb.Estimator(w * factor, h * factor, ss, bs, chunk_pairs=2, collect_stats=True) as est:
+        got = est.estimate_upsampled([f1, g1], [f2, g2], factor)
+        shape = est.shape
+        lvl0 = est.level_image(0, 0)
+    py, px = shape["padding_y"], shape["padding_x"]
+    up = oracle.resize_linear(f1, factor)
+    assert np.array_equal(lvl0[py:py + h * factor, px:px + w * factor], up)
+    for (a, b), g in (((f1, f2), got[0]), ((g1, g2), got[1])):
+        dense, _ = oracle.estimate(oracle.resize_linear(a, factor), oracle.resize_linear(b, factor), ss, bs, 2)
+        want = oracle.strip_subsample(dense, px, py, factor)
+        assert g.shape == (h, w, 2)
+        assert np.array_equal(g, want), describe_diff(g, want)
+
+
 # ------------------------------------------------------------------------------------------ full size (BASELINE configs)
 def test_config0_rubberwhale_standin_default_parameters(oracle, tmp_path):
     """BASELINE config 0: RubberWhale (584x388) through main()'s pipeline with the repo's defaults -- x4 bilinear
@@ -267,6 +305,14 @@ def test_config0_rubberwhale_standin_default_parameters(oracle, tmp_path):
     sub_oracle = np.ascontiguousarray(want[py:shape["padded_height"] - py:4, px:shape["padded_width"] - px:4] / 4.0)
     assert aee == oracle.aee(gt, sub_oracle)
     assert aee < 0.25, aee  # sanity: the stand-in's motion IS the ground truth, quarter-pel vectors should be close
+    # the same pair through main()'s wrapper on the device (cv::resize arithmetic instead of the stand-in resampler):
+    # up-sampling, MF and the strip / sub-sample all on the GPU, checked against the oracle chain
+    o1, o2 = oracle.resize_linear(d["frame10"], 4), oracle.resize_linear(d["frame11"], 4)
+    with bb.Estimator(4 * 584, 4 * 388, ss, bs) as est:
+        qp = est.estimate_upsampled(d["frame10"], d["frame11"], 4)
+    want_qp = oracle.strip_subsample(oracle.estimate(o1, o2, ss, bs, 2)[0], px, py, 4)
+    assert np.array_equal(qp, want_qp), describe_diff(qp, want_qp)
+    assert fl.CalculateMSE(gt, qp) < 0.25
     out = tmp_path / "rubberwhale.flo"
     fl.WriteFlowFile(sub, out)
     assert np.array_equal(fl.ReadFlowFile(out), sub)

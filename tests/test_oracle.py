@@ -168,3 +168,39 @@ def test_config0_rubberwhale_standin_on_the_oracle(oracle):
     assert sub.shape == d["gt"].shape
     aee = oracle.aee(d["gt"], sub)
     assert aee == pytest.approx(0.13334927018152679, rel=0, abs=1e-9)
+
+
+# ------------------------------------------------------------------------------------------ main()'s quarter-pel wrapper
+def test_resize_linear_equals_cv2_golden(oracle):
+    """cv::resize(INTER_LINEAR) of main_class.cpp:32-33: the oracle's restatement against outputs of the container's cv2
+    (tests/golden/make_resize_golden.py), and against cv2 itself where it is importable."""
+    d = np.load(os.path.join(GOLD, "resize_cv2.npz"))
+    n = len([k for k in d.files if k.startswith("in_")])
+    assert n >= 5
+    for i in range(n):
+        f = int(d[f"factor_{i}"][0])
+        got = oracle.resize_linear(d[f"in_{i}"], f)
+        assert np.array_equal(got, d[f"out_{i}"]), (i, f, int((got != d[f"out_{i}"]).sum()))
+    try:
+        import cv2
+    except ImportError:
+        return
+    rng = np.random.default_rng(77)
+    for (h, w), f in [((31, 45), 4), ((64, 50), 2), ((17, 23), 8), ((388, 584), 4)]:
+        a = rng.integers(0, 256, (h, w)).astype(np.uint8)
+        assert np.array_equal(oracle.resize_linear(a, f), cv2.resize(a, None, fx=f, fy=f, interpolation=cv2.INTER_LINEAR))
+
+
+def test_strip_subsample_follows_main(oracle):
+    """main_class.cpp:58-70 -- literal loop in numpy against the oracle and against the product's host helper."""
+    import blockbasedmotionestimation_b200 as bb
+    rng = np.random.default_rng(5)
+    shape = bb.plan_shape(4 * 73, 4 * 41, [24, 24], [8, 8])
+    ph, pw, px, py = shape["padded_height"], shape["padded_width"], shape["padding_x"], shape["padding_y"]
+    flow = rng.integers(-40, 41, (ph, pw, 2)).astype(np.float32)
+    want = np.zeros((41, 73, 2), np.float32)
+    for i in range(py, ph - py, 4):
+        for j in range(px, pw - px, 4):
+            want[(i - py) // 4, (j - px) // 4] = flow[i, j] / np.float32(4)
+    assert np.array_equal(oracle.strip_subsample(flow, px, py, 4), want)
+    assert np.array_equal(bb.Flow().StripAndSubsample(flow, shape, 4), want)
