@@ -57,6 +57,9 @@ SIGNATURES = {
     "bbme_estimate": (_I, [_P, _P, _P, _SZ, _P]),
     "bbme_estimate_batch": (_I, [_P, _I, C.POINTER(_P), C.POINTER(_P), _SZ, C.POINTER(_P)]),
     "bbme_estimate_batch_async": (_I, [_P, _I, C.POINTER(_P), C.POINTER(_P), _SZ, C.POINTER(_P)]),
+    "bbme_estimate_sequence": (_I, [_P, _I, C.POINTER(_P), _SZ, C.POINTER(_P)]),
+    "bbme_estimate_sequence_async": (_I, [_P, _I, C.POINTER(_P), _SZ, C.POINTER(_P)]),
+    "bbme_estimate_sequence_device": (_I, [_P, _I, _P, _SZ, _SZ, _P, _SZ]),
     "bbme_estimate_upsampled": (_I, [_P, _I, _I, C.POINTER(_P), C.POINTER(_P), _SZ, C.POINTER(_P)]),
     "bbme_estimate_upsampled_async": (_I, [_P, _I, _I, C.POINTER(_P), C.POINTER(_P), _SZ, C.POINTER(_P)]),
     "bbme_estimate_upsampled_device": (_I, [_P, _I, _I, _P, _P, _SZ, _SZ, _P, _SZ]),

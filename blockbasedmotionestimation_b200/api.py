@@ -162,6 +162,31 @@ class Estimator:
         _check(self._lib, self._ctx, self._lib.bbme_estimate_batch(self._ctx, n, p1, p2, pitch, po), "bbme_estimate_batch")
         return out_list
 
+    # -- video sequences: n frames -> n - 1 pairs (t, t + 1), every frame's pyramid built once
+    def estimate_sequence(self, frames):
+        n = len(frames)
+        if n < 2:
+            raise BbmeError(-1, "a sequence needs at least two frames")
+        h, w = self.shape["height"], self.shape["width"]
+        PA = C.c_void_p * n
+        pf, po = PA(), PA()
+        outs = [np.empty(self.flow_shape(), np.float32) for _ in range(n - 1)]
+        keep = []
+        for i in range(n):
+            a = np.ascontiguousarray(frames[i])
+            if a.dtype != np.uint8 or a.shape != (h, w):
+                raise BbmeError(-1, f"frames must be uint8 {h}x{w}")
+            keep.append(a)
+            pf[i] = a.ctypes.data
+            po[i] = outs[i].ctypes.data if i < n - 1 else None
+        _check(self._lib, self._ctx, self._lib.bbme_estimate_sequence(self._ctx, n, pf, w, po), "bbme_estimate_sequence")
+        return outs
+
+    def estimate_sequence_device(self, n_frames, d_frames, pitch, plane, d_flow, flow_plane):
+        _check(self._lib, self._ctx,
+               self._lib.bbme_estimate_sequence_device(self._ctx, int(n_frames), C.c_void_p(d_frames), int(pitch), int(plane),
+                                                       C.c_void_p(d_flow), int(flow_plane)), "bbme_estimate_sequence_device")
+
     # -- main()'s quarter-pel wrapper on the device (main_class.cpp:32-33, 58-70)
     def estimate_upsampled(self, im1_list, im2_list, factor=4):
         """Frames of (height / factor) x (width / factor) -- width, height as planned -- are up-sampled with

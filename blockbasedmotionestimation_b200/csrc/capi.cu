@@ -37,6 +37,7 @@ struct Slot {
   uint32_t* hist = nullptr;                // BBME_FIX_HIST=1: kHistSweeps x 64 words (RegArgs::hist)
   float* out = nullptr;
   TmaSearchPlan tma[kMaxLevels];
+  TmaSearchPlan tma_seq[kMaxLevels];  // sequence mode: image 2 of pair i is plane i + 1 of the image-1 array
   std::vector<cudaEvent_t> ev;
   std::vector<int> ev_tag;
   int last_n = 0;
@@ -201,7 +202,7 @@ void fold_events(bbme_ctx* c, Slot& s) {
 // factor) and are up-sampled on the way in; d_flow then receives the stripped, sub-sampled, divided field.
 int run_chunk(bbme_ctx* c, Slot& s, int n, const uint8_t* d_in1, const uint8_t* d_in2, size_t in_pitch,
               size_t in_plane, float* d_flow, size_t flow_plane, int16_t* d_compact, size_t compact_plane,
-              int factor = 1) {
+              int factor = 1, bool seq = false) {
   const bbme_shape& sh = c->shape;
   const int L = sh.num_levels;
   cudaStream_t st = s.stream;
@@ -209,20 +210,31 @@ int run_chunk(bbme_ctx* c, Slot& s, int n, const uint8_t* d_in1, const uint8_t* 
   s.last_n = n > s.last_n ? n : s.last_n;
   mark(c, s, TAG_BEGIN);
   // ---- MF::MF: pad + Gaussian pyramid (motion_framework.cpp:57-106)
+  // Sequence mode (n pairs from n + 1 consecutive frames at d_in1): every frame is padded and down-sampled once, into
+  // plane f of the image-1 array; pair i reads planes i and i + 1.  The two-frames-per-pair kernels do that unchanged
+  // when "pair" p is handed frames 2p and 2p + 1 (pair stride = two planes); with an even n the last launch slot works
+  // on a spare plane that nobody reads.
+  const int npf = seq ? (n + 2) / 2 : n;  // launch slots of the pad / pyrDown kernels
+  uint8_t* img2_l0 = seq ? s.img[0][0] + c->plane[0] : s.img[1][0];
   if (factor > 1) {
     ResizeTaps taps;
     if (make_resize_taps(factor, &taps) != 0) return fail(c, BBME_E_ARG, "up-sampling factor %d (supported: 2, 4, 8)", factor);
-    launch_resize_pad(d_in1, d_in2, in_pitch, in_plane, sh.width / factor, sh.height / factor, taps, sh.padding_x,
-                      sh.padding_y, s.img[0][0], s.img[1][0], c->pitch[0], c->plane[0], sh.padded_height, n, st);
+    launch_resize_pad(d_in1, seq ? d_in1 + in_plane : d_in2, in_pitch, seq ? 2 * in_plane : in_plane, sh.width / factor,
+                      sh.height / factor, taps, sh.padding_x, sh.padding_y, s.img[0][0], img2_l0, c->pitch[0],
+                      seq ? 2 * c->plane[0] : c->plane[0], sh.padded_height, npf, st);
   } else {
-    launch_pad(d_in1, d_in2, in_pitch, in_plane, sh.width, sh.height, sh.padding_x, sh.padding_y, s.img[0][0],
-               s.img[1][0], c->pitch[0], c->plane[0], sh.padded_width, sh.padded_height, n, st);
+    launch_pad(d_in1, seq ? d_in1 + in_plane : d_in2, in_pitch, seq ? 2 * in_plane : in_plane, sh.width, sh.height,
+               sh.padding_x, sh.padding_y, s.img[0][0], img2_l0, c->pitch[0], seq ? 2 * c->plane[0] : c->plane[0],
+               sh.padded_width, sh.padded_height, npf, st);
   }
   ++c->launches;
   for (int l = 1; l < L; ++l) {
-    ImgView a{s.img[0][l - 1], sh.level_width[l - 1], sh.level_height[l - 1], c->pitch[l - 1], c->plane[l - 1]};
-    ImgView b{s.img[1][l - 1], sh.level_width[l - 1], sh.level_height[l - 1], c->pitch[l - 1], c->plane[l - 1]};
-    launch_pyrdown(a, b, s.img[0][l], s.img[1][l], c->pitch[l], c->plane[l], n, st);
+    const size_t sp = seq ? 2 * c->plane[l - 1] : c->plane[l - 1];
+    ImgView a{s.img[0][l - 1], sh.level_width[l - 1], sh.level_height[l - 1], c->pitch[l - 1], sp};
+    ImgView b{seq ? s.img[0][l - 1] + c->plane[l - 1] : s.img[1][l - 1], sh.level_width[l - 1], sh.level_height[l - 1],
+              c->pitch[l - 1], sp};
+    launch_pyrdown(a, b, s.img[0][l], seq ? s.img[0][l] + c->plane[l] : s.img[1][l], c->pitch[l],
+                   seq ? 2 * c->plane[l] : c->plane[l], npf, st);
     ++c->launches;
   }
   mark(c, s, TAG_PYR);
@@ -232,7 +244,7 @@ int run_chunk(bbme_ctx* c, Slot& s, int n, const uint8_t* d_in1, const uint8_t* 
     const int bs0 = sh.block_size[l];
     const int R = radius_of(sh.search_size[l], bs0);
     ImgView i1{s.img[0][l], lw, lh, c->pitch[l], c->plane[l]};
-    ImgView i2{s.img[1][l], lw, lh, c->pitch[l], c->plane[l]};
+    ImgView i2{seq ? s.img[0][l] + c->plane[l] : s.img[1][l], lw, lh, c->pitch[l], c->plane[l]};
     short2* cur = s.mv_a[l];
     short2* nxt = s.mv_b[l];
     int g = bs0, gw = lw / g, gh = lh / g;
@@ -244,9 +256,10 @@ int run_chunk(bbme_ctx* c, Slot& s, int n, const uint8_t* d_in1, const uint8_t* 
       ++c->launches;
     }
     mark(c, s, TAG_OTHER);
-    const bool use_tma = s.tma[l].supported && c->opt.search_kernel != 1;
+    const TmaSearchPlan& tplan = seq ? s.tma_seq[l] : s.tma[l];
+    const bool use_tma = tplan.supported && c->opt.search_kernel != 1;
     unsigned long long* ctrs = c->opt.collect_stats ? s.counters : nullptr;
-    if (use_tma) launch_search_tma(s.tma[l], i1, i2, field, n, ctrs, c->sm_count, st);
+    if (use_tma) launch_search_tma(tplan, i1, i2, field, n, ctrs, c->sm_count, st);
     else launch_search_generic(i1, i2, field, g, R, n, ctrs, st);
     ++c->launches;
     ++c->search_launches;
@@ -481,10 +494,11 @@ int bbme_plan(bbme_ctx* c, int width, int height, int num_levels, const int* sea
   c->slots.resize(o.slots);
   for (Slot& s : c->slots) {
     CUDA_TRY(c, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-    if ((rc = dev_alloc(c, &s.in1, n * c->in_plane, false)) || (rc = dev_alloc(c, &s.in2, n * c->in_plane, false))) return rc;
+    // image-1 side buffers hold two spare planes: sequence mode keeps n + 1 frames there (+1 for an odd launch slot)
+    if ((rc = dev_alloc(c, &s.in1, (n + 2) * c->in_plane, false)) || (rc = dev_alloc(c, &s.in2, n * c->in_plane, false))) return rc;
     for (int l = 0; l < L; ++l) {
       for (int f = 0; f < 2; ++f)
-        if ((rc = dev_alloc(c, &s.img[f][l], n * c->plane[l], true))) return rc;
+        if ((rc = dev_alloc(c, &s.img[f][l], (f == 0 ? n + 2 : n) * c->plane[l], true))) return rc;
       if ((rc = dev_alloc(c, &s.mv_a[l], n * c->cap[l], true)) || (rc = dev_alloc(c, &s.mv_b[l], n * c->cap[l], true))) return rc;
       if (o.keep_search_mv) {
         const size_t blocks = (size_t)(sh.level_width[l] / sh.block_size[l]) * (sh.level_height[l] / sh.block_size[l]);
@@ -500,12 +514,17 @@ int bbme_plan(bbme_ctx* c, int width, int height, int num_levels, const int* sea
     if (getenv("BBME_FIX_HIST") && (rc = dev_alloc(c, &s.hist, (size_t)kHistSweeps * 64, true))) return rc;
     for (int l = 0; l < L; ++l) {
       memset(&s.tma[l], 0, sizeof(s.tma[l]));
+      memset(&s.tma_seq[l], 0, sizeof(s.tma_seq[l]));
       if (o.search_kernel == 1) continue;
       char msg[256] = {0};
       const int R = radius_of(sh.search_size[l], sh.block_size[l]);
       int trc = tma_search_plan(&s.tma[l], s.img[0][l], s.img[1][l], sh.level_width[l], sh.level_height[l], c->pitch[l],
                                 c->plane[l], o.chunk_pairs, sh.block_size[l], R, msg, sizeof(msg));
       if (trc != 0) return fail(c, BBME_E_CUDA, "TMA search plan failed at level %d: %s", l, msg);
+      if (trc == 0)
+        trc = tma_search_plan(&s.tma_seq[l], s.img[0][l], s.img[0][l] + c->plane[l], sh.level_width[l], sh.level_height[l],
+                              c->pitch[l], c->plane[l], o.chunk_pairs, sh.block_size[l], R, msg, sizeof(msg));
+      if (trc != 0) return fail(c, BBME_E_CUDA, "TMA search plan (sequence mode) failed at level %d: %s", l, msg);
       if (o.search_kernel == 2 && !s.tma[l].supported)
         return fail(c, BBME_E_ARG, "search_kernel=2 but level %d (block %d, R %d) is not covered by the TMA kernel", l,
                     sh.block_size[l], R);
@@ -622,6 +641,73 @@ int bbme_estimate_upsampled(bbme_ctx* c, int n, int factor, const uint8_t* const
   rc = sync_all(c);
   if (rc) return rc;
   return collect_after_sync(c);
+}
+
+// A video sequence: n_frames frames are n_frames - 1 pairs (t, t + 1).  Chunks of chunk_pairs pairs take chunk_pairs + 1
+// frames; consecutive chunks share one frame (uploaded and down-sampled again, 1 / chunk_pairs of the work).
+int bbme_estimate_sequence_async(bbme_ctx* c, int n_frames, const uint8_t* const* frames, size_t pitch, float* const* flow) {
+  if (!c) return BBME_E_ARG;
+  if (!c->planned) return fail(c, BBME_E_STATE, "bbme_estimate_sequence before bbme_plan");
+  if (n_frames < 2 || !frames || !flow || pitch < (size_t)c->shape.width) return fail(c, BBME_E_ARG, "bbme_estimate_sequence: bad arguments");
+  for (int i = 0; i < n_frames; ++i)
+    if (!frames[i] || (i + 1 < n_frames && !flow[i])) return fail(c, BBME_E_ARG, "bbme_estimate_sequence: null buffer at frame %d", i);
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  begin_call(c);
+  const int chunk = c->opt.chunk_pairs, n = n_frames - 1;
+  const size_t flow_bytes = c->out_plane * sizeof(float);
+  int ci = c->next_slot;
+  for (int start = 0; start < n; start += chunk, ++ci) {
+    Slot& s = c->slots[ci % c->slots.size()];
+    const int m = (n - start < chunk) ? (n - start) : chunk;
+    for (int i = 0; i <= m; ++i)
+      CUDA_TRY(c, cudaMemcpy2DAsync(s.in1 + (size_t)i * c->in_plane, c->in_pitch, frames[start + i], pitch, c->shape.width,
+                                    c->shape.height, cudaMemcpyHostToDevice, s.stream));
+    int rc = run_chunk(c, s, m, s.in1, nullptr, c->in_pitch, c->in_plane, s.out, c->out_plane, nullptr, 0, 1, true);
+    if (rc) return rc;
+    for (int i = 0; i < m; ++i)
+      CUDA_TRY(c, cudaMemcpyAsync(flow[start + i], s.out + (size_t)i * c->out_plane, flow_bytes, cudaMemcpyDeviceToHost, s.stream));
+  }
+  c->next_slot = ci % (int)c->slots.size();
+  return BBME_OK;
+}
+
+int bbme_estimate_sequence(bbme_ctx* c, int n_frames, const uint8_t* const* frames, size_t pitch, float* const* flow) {
+  int rc = bbme_estimate_sequence_async(c, n_frames, frames, pitch, flow);
+  if (rc) return rc;
+  rc = sync_all(c);
+  if (rc) return rc;
+  return collect_after_sync(c);
+}
+
+int bbme_estimate_sequence_device(bbme_ctx* c, int n_frames, const uint8_t* d_frames, size_t pitch, size_t plane,
+                                  float* d_flow, size_t flow_plane) {
+  if (!c) return BBME_E_ARG;
+  if (!c->planned) return fail(c, BBME_E_STATE, "bbme_estimate_sequence_device before bbme_plan");
+  if (n_frames < 2 || !d_frames || !d_flow || pitch < (size_t)c->shape.width || plane < pitch * (size_t)c->shape.height ||
+      flow_plane < c->out_plane)
+    return fail(c, BBME_E_ARG, "bbme_estimate_sequence_device: bad arguments");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  begin_call(c);
+  const int chunk = c->opt.chunk_pairs, n = n_frames - 1;
+  int ci = 0;
+  for (int start = 0; start < n; start += chunk, ++ci) {
+    Slot& s = c->slots[ci % c->slots.size()];
+    const int m = (n - start < chunk) ? (n - start) : chunk;
+    // an even m makes the pad kernel's last launch slot read one frame past frame start + m: stage through the slot
+    // buffer when that frame does not exist (end of the sequence)
+    const uint8_t* src = d_frames + (size_t)start * plane;
+    size_t sp = pitch, spl = plane;
+    if ((m & 1) == 0 && start + m + 1 >= n_frames) {
+      CUDA_TRY(c, cudaMemcpy2DAsync(s.in1, c->in_pitch, src, pitch, c->shape.width, (size_t)c->shape.height, cudaMemcpyDeviceToDevice, s.stream));
+      for (int i = 1; i <= m; ++i)
+        CUDA_TRY(c, cudaMemcpy2DAsync(s.in1 + (size_t)i * c->in_plane, c->in_pitch, src + (size_t)i * plane, pitch, c->shape.width,
+                                      (size_t)c->shape.height, cudaMemcpyDeviceToDevice, s.stream));
+      src = s.in1; sp = c->in_pitch; spl = c->in_plane;
+    }
+    int rc = run_chunk(c, s, m, src, nullptr, sp, spl, d_flow + (size_t)start * flow_plane, flow_plane, nullptr, 0, 1, true);
+    if (rc) return rc;
+  }
+  return BBME_OK;
 }
 
 int bbme_estimate_batch(bbme_ctx* c, int n, const uint8_t* const* im1, const uint8_t* const* im2, size_t pitch,

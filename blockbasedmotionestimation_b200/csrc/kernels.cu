@@ -371,34 +371,69 @@ __global__ void __launch_bounds__(256) k_divide(const short2* __restrict__ in, i
   out[(size_t)pair * out_plane + i] = in[(size_t)pair * in_plane + (size_t)(y >> 1) * gw + (x >> 1)];
 }
 
+// Same, two input entries per thread: one 8-byte load, two 16-byte stores (the rows 2y and 2y + 1 of the finer grid are
+// identical).  Needs an even grid width and 16-byte aligned planes.
+__global__ void __launch_bounds__(256) k_divide2(const short2* __restrict__ in, int gw, int gh, size_t in_plane,
+                                                 short2* __restrict__ out, size_t out_plane) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // pair of input entries
+  const int pair = blockIdx.y;
+  const int hw = gw >> 1;
+  if (i >= hw * gh) return;
+  const int x2 = i % hw, y = i / hw;
+  const uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint32_t*>(in + (size_t)pair * in_plane) + (size_t)y * gw + 2 * x2);
+  const uint4 o = make_uint4(v.x, v.x, v.y, v.y);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(out + (size_t)pair * out_plane) + (size_t)(2 * y) * (2 * gw) + 4 * x2;
+  *reinterpret_cast<uint4*>(dst) = o;
+  *reinterpret_cast<uint4*>(dst + 2 * gw) = o;
+}
+
 void launch_divide(const short2* in, int gw, int gh, size_t in_plane, short2* out, size_t out_plane, int n,
                    cudaStream_t s) {
-  dim3 grid((4 * gw * gh + 255) / 256, n);
-  k_divide<<<grid, 256, 0, s>>>(in, gw, gh, in_plane, out, out_plane);
+  const bool vec = (gw & 1) == 0 && (in_plane & 1) == 0 && (out_plane & 3) == 0 &&
+                   (reinterpret_cast<uintptr_t>(in) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (vec) {
+    dim3 grid((gw / 2 * gh + 255) / 256, n);
+    k_divide2<<<grid, 256, 0, s>>>(in, gw, gh, in_plane, out, out_plane);
+  } else {
+    dim3 grid((4 * gw * gh + 255) / 256, n);
+    k_divide<<<grid, 256, 0, s>>>(in, gw, gh, in_plane, out, out_plane);
+  }
 }
 
 // Final dense field (motion_framework.cpp:205-206, 815-826, 218): CV_32FC2, every 2x2 block shares one MV.
-// One thread = two horizontally adjacent pixels = one 16-byte store; HBM-write-bound (8 B / pixel).
-__global__ void __launch_bounds__(256) k_export(const short2* __restrict__ mv2, int gw2, size_t mv_plane,
-                                                float* __restrict__ out, int pw, int ph, size_t out_plane) {
-  const int x2 = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y;
-  const int pair = blockIdx.z;
-  if (x2 >= gw2 || y >= ph) return;
-  const short2 m = __ldg(&mv2[(size_t)pair * mv_plane + (size_t)(y >> 1) * gw2 + x2]);
-  const float u = (float)m.x, v = (float)m.y;
-  float* o = out + (size_t)pair * out_plane + ((size_t)y * pw + 2 * x2) * 2;
-  if ((reinterpret_cast<uintptr_t>(o) & 15) == 0) {
-    __stcs(reinterpret_cast<float4*>(o), make_float4(u, v, u, v));
-  } else {
-    o[0] = u; o[1] = v; o[2] = u; o[3] = v;
+// One thread = one entry of the 2x2-granular field = one 16-byte streaming store into each of the two pixel rows it
+// covers; a CTA walks over (pair, entry row) pairs, so the grid is a few waves instead of a million tiny CTAs.
+// HBM-write-bound (8 B / pixel).
+__global__ void __launch_bounds__(256) k_export(const short2* __restrict__ mv2, int gw2, int gh2, size_t mv_plane,
+                                                float* __restrict__ out, int pw, size_t out_plane, int n) {
+  const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (out_plane & 3) == 0 && (pw & 1) == 0;
+  for (int row = blockIdx.x; row < n * gh2; row += gridDim.x) {
+    const int pair = row / gh2, y2 = row - pair * gh2;
+    const short2* src = mv2 + (size_t)pair * mv_plane + (size_t)y2 * gw2;
+    float* o0 = out + (size_t)pair * out_plane + (size_t)(2 * y2) * pw * 2;
+    float* o1 = o0 + (size_t)pw * 2;
+    for (int x2 = threadIdx.x; x2 < gw2; x2 += blockDim.x) {
+      const short2 m = __ldg(&src[x2]);
+      const float u = (float)m.x, v = (float)m.y;
+      if (aligned) {
+        __stcs(reinterpret_cast<float4*>(o0 + 4 * x2), make_float4(u, v, u, v));
+        __stcs(reinterpret_cast<float4*>(o1 + 4 * x2), make_float4(u, v, u, v));
+      } else {
+        float* a = o0 + 4 * x2;
+        float* b = o1 + 4 * x2;
+        a[0] = u; a[1] = v; a[2] = u; a[3] = v;
+        b[0] = u; b[1] = v; b[2] = u; b[3] = v;
+      }
+    }
   }
 }
 
 void launch_export(const short2* mv2, int gw2, size_t mv_plane, float* out, int pw, int ph, size_t out_plane, int n,
                    cudaStream_t s) {
-  dim3 grid((gw2 + 127) / 128, ph, n);
-  k_export<<<grid, 128, 0, s>>>(mv2, gw2, mv_plane, out, pw, ph, out_plane);
+  const int gh2 = ph / 2;
+  long long rows = (long long)n * gh2;
+  int grid = (int)(rows < 148 * 16 ? rows : 148 * 16);
+  k_export<<<grid, 256, 0, s>>>(mv2, gw2, gh2, mv_plane, out, pw, out_plane, n);
 }
 
 __global__ void __launch_bounds__(256) k_export_compact(const short2* __restrict__ mv2, int count, size_t mv_plane,

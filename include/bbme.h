@@ -128,6 +128,19 @@ int bbme_estimate_upsampled(bbme_ctx* ctx, int n, int factor, const uint8_t* con
 int bbme_estimate_upsampled_async(bbme_ctx* ctx, int n, int factor, const uint8_t* const* im1,
                                   const uint8_t* const* im2, size_t pitch_bytes, float* const* flow);
 
+/* A video sequence (stream frames, reuse pyramids): n_frames consecutive frames are n_frames - 1 pairs
+ * (frame t, frame t + 1), i.e. what a caller looping `MF(frame[t], frame[t+1], ...)` over a clip computes.  Every frame
+ * is uploaded, padded and down-sampled ONCE and serves as image 2 of pair t - 1 and as image 1 of pair t.  flow[t]
+ * (t < n_frames - 1) receives the padded dense field of pair t; flow[n_frames - 1] is not read.  Results are identical
+ * to bbme_estimate_batch on the same pairs. */
+int bbme_estimate_sequence(bbme_ctx* ctx, int n_frames, const uint8_t* const* frames, size_t pitch_bytes,
+                           float* const* flow);
+int bbme_estimate_sequence_async(bbme_ctx* ctx, int n_frames, const uint8_t* const* frames, size_t pitch_bytes,
+                                 float* const* flow);
+/* Frames and fields in device memory: n_frames planes of plane_stride bytes, n_frames - 1 flow planes. */
+int bbme_estimate_sequence_device(bbme_ctx* ctx, int n_frames, const uint8_t* d_frames, size_t pitch_bytes,
+                                  size_t plane_stride, float* d_flow, size_t flow_plane_stride);
+
 /* n <= chunk_pairs pairs already in device memory (same device as the context).  Frames are n planes of
  * `plane_stride` bytes; flow is n planes of flow_plane_stride floats.  Runs on slot 0's stream and returns
  * after enqueueing; call bbme_sync before reading.  This is the "inputs resident in HBM" entry point. */

@@ -240,6 +240,35 @@ def test_plan_errors_are_loud():
             est.estimate(np.zeros((96, 64), np.uint8), np.zeros((96, 64), np.uint8))
 
 
+# ------------------------------------------------------------------------------------------ video sequences
+@pytest.mark.parametrize("chunk", [1, 2, 3, 8])
+def test_sequence_equals_pairs(oracle, chunk):
+    """n frames -> n - 1 pairs with every frame's pyramid built once: identical to the pair-wise path
+    and to the oracle, for chunk sizes that split the sequence evenly, unevenly and not at all; host and device entry
+    points."""
+    import torch
+    h, w, ss, bs = 96, 160, [24, 24], [8, 8]
+    a0, a1 = make_pair(h, w, 71, shift=(2, -1), max_patch_shift=3)
+    b0, b1 = make_pair(h, w, 72, shift=(-2, 2), max_patch_shift=3)
+    frames = [a0, a1, b0, b1, a0, b1]
+    with bb.Estimator(w, h, ss, bs, chunk_pairs=chunk, slots=2) as est:
+        seq = est.estimate_sequence(frames)
+        pairs = est.estimate_batch(frames[:-1], frames[1:])
+        dfr = torch.from_numpy(np.stack(frames)).cuda()
+        Hp, Wp = est.flow_shape()[:2]
+        dfl = torch.zeros((len(frames) - 1, Hp, Wp, 2), dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        est.estimate_sequence_device(len(frames), dfr.data_ptr(), w, w * h, dfl.data_ptr(), Hp * Wp * 2)
+        est.sync()
+        dev = dfl.cpu().numpy()
+    assert len(seq) == len(frames) - 1
+    for t in range(len(frames) - 1):
+        assert np.array_equal(seq[t], pairs[t]), (t, describe_diff(seq[t], pairs[t]))
+        assert np.array_equal(dev[t], pairs[t]), (t, describe_diff(dev[t], pairs[t]))
+    want, _ = oracle.estimate(frames[2], frames[3], ss, bs, 2)
+    assert np.array_equal(seq[2], want), describe_diff(seq[2], want)
+
+
 # ------------------------------------------------------------------------------------------ main()'s quarter-pel wrapper
 @pytest.mark.parametrize("shape,factor", [((37, 53), 4), ((33, 47), 2), ((20, 30), 8), ((97, 146), 4), ((2, 3), 4), ((388, 584), 4)])
 def test_resize_matches_oracle(gpu, oracle, shape, factor):
