@@ -291,9 +291,9 @@ def run_ours(args, rank, local_rank, world):
         "algorithmic_absdiffs_per_launch": absdiffs / n_search,
         "avg_launch_ms": ms_search / n_search, "launches_per_step": n_search,
         # dram__bytes_read.sum + dram__bytes_write.sum of the level-0 launch (128 pairs) from the committed ncu capture
-        # profiles/r01_search_l0_ncu.txt (not re-measured here); algorithmic bytes of that launch: 2 frames x 2.09 MB x 128
-        "traffic": 860.6e6 if P == 128 else None,
-        "traffic_note": "bytes per level-0 launch of 128 pairs (ncu --set full, profiles/r01_search_l0_ncu.txt); algorithmic 535 MB",
+        # profiles/r01b_search_l0_ncu.txt (not re-measured here); algorithmic bytes of that launch: 2 frames x 2.09 MB x 128
+        "traffic": 862.3e6 if P == 128 else None,
+        "traffic_note": "bytes per level-0 launch of 128 pairs (ncu --set full, profiles/r01b_search_l0_ncu.txt); algorithmic 535 MB + 4 MB of vectors",
     }
     roofline_hbm = {
         "bound": "hbm", "algorithmic_bytes_per_pair": alg_bytes_pair,
