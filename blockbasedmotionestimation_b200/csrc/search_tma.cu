@@ -307,6 +307,8 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
     const int qq = active ? q : 0;
     const int sidx = qq / a.n, o = qq - sidx * a.n;
     uint32_t best = 0xffffffffu, best_rank = 0xffffffffu;  // K64: best = SAD, best_rank = its spiral rank
+    uint32_t eqmask = 0;   // K64: the lane's candidates that attain `best`
+    int rank_dx = 0, rank_dy0 = 0;
 
     if (__any_sync(0xffffffffu, active)) {
       const int bo = m.off + o;                 // byte column of this lane's displacement inside the staged box
@@ -366,15 +368,21 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
       const int c_lo = max(0, -(m.y2 + dyf));                 // py >= 0
       const int c_hi = min(min(SEG - 1, a.R - dyf), a.h - BS - m.y2 - dyf);  // dy <= R and py + BS <= h
       if (K64) {
-        // 64-bit key: (SAD, spiral rank), the rank computed from (dx, dy); kept as two words until the reduction
+        // 64-bit key (SAD, spiral rank).  The closed-form rank costs ~25 instructions, so it is NOT computed per
+        // candidate: the lane keeps its minimum SAD and the set of candidates attaining it; after the warp has reduced
+        // the SADs, only the lanes that hold the item's minimum rank their (usually single) candidate.
 #pragma unroll
         for (int c = 0; c < SEG; ++c) {
-          const uint32_t rank = spiral_rank(dx, dyf + c);
           const bool ok = xok && c >= c_lo && c <= c_hi;
-          const bool better = ok && (acc[c] < best || (acc[c] == best && rank < best_rank));
-          best = better ? acc[c] : best;
-          best_rank = better ? rank : best_rank;
+          best = min(best, ok ? acc[c] : 0xffffffffu);
         }
+#pragma unroll
+        for (int c = 0; c < SEG; ++c) {
+          const bool ok = xok && c >= c_lo && c <= c_hi;
+          eqmask |= (ok && acc[c] == best) ? (1u << c) : 0u;
+        }
+        rank_dx = dx;
+        rank_dy0 = dyf;
       } else {
         const uint16_t* rk = s_rank + (size_t)(m.band * a.band_rows + cy0) * a.n + o;
         if (xok && c_lo == 0 && c_hi == SEG - 1) {
@@ -396,6 +404,11 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
     uint32_t b1 = __reduce_min_sync(0xffffffffu, second ? best : 0xffffffffu);
     uint32_t r0 = 0, r1 = 0;
     if (K64) {  // among the lanes holding the minimum SAD, the smallest rank
+      const uint32_t mine = second ? b1 : b0;
+      if (best == mine && best != 0xffffffffu) {
+        for (uint32_t mm = eqmask; mm; mm &= mm - 1u)
+          best_rank = min(best_rank, spiral_rank(rank_dx, rank_dy0 + __ffs(mm) - 1));
+      }
       r0 = __reduce_min_sync(0xffffffffu, (!second && best == b0) ? best_rank : 0xffffffffu);
       r1 = __reduce_min_sync(0xffffffffu, (second && best == b1) ? best_rank : 0xffffffffu);
     }
