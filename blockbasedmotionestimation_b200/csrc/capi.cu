@@ -41,6 +41,15 @@ struct Slot {
   std::vector<cudaEvent_t> ev;
   std::vector<int> ev_tag;
   int last_n = 0;
+  // CUDA graphs of the per-chunk kernel sequence, keyed by everything run_chunk's launches depend on
+  struct GraphEntry {
+    int n, factor, seq;
+    const void *in1, *in2, *flow, *compact;
+    size_t in_pitch, in_plane, flow_plane, compact_plane;
+    cudaGraphExec_t exec;
+    uint32_t launches, search_launches;  // kernels inside the graph (for the stats)
+  };
+  std::vector<GraphEntry> graphs;
 };
 
 constexpr int kHistSweeps = 256;
@@ -67,6 +76,7 @@ struct bbme_ctx {
   uint32_t launches = 0;
   uint32_t search_launches = 0;
   bool stats_armed = false;
+  int use_graphs = 1;   // small chunks replay a captured CUDA graph of their ~70-230 launches (BBME_GRAPHS=0 disables)
   int next_slot = 0;    // round-robin position over the slots across asynchronous calls
   int grid_rounds = -1;  // fix-up rounds run grid-wide before the per-pair tail loop; -1 = by chunk size (BBME_GRID_ROUNDS)
 };
@@ -112,6 +122,8 @@ int dev_alloc(bbme_ctx* c, T** p, size_t count, bool zero) {
 void release_plan(bbme_ctx* c) {
   for (Slot& s : c->slots) {
     for (cudaEvent_t e : s.ev) cudaEventDestroy(e);
+    for (auto& g : s.graphs) cudaGraphExecDestroy(g.exec);
+    s.graphs.clear();
     if (s.stream && s.own_stream) cudaStreamDestroy(s.stream);
   }
   c->slots.clear();
@@ -331,6 +343,54 @@ int run_chunk(bbme_ctx* c, Slot& s, int n, const uint8_t* d_in1, const uint8_t* 
   return BBME_OK;
 }
 
+// run_chunk through a CUDA graph.  A chunk is 70-230 dependent launches, most of them a few microseconds long: for small
+// chunks (a single pair above all) the host's launch calls and the gaps between dependent kernels are a large part of the
+// latency.  The launch sequence has no host-side decisions, so it is captured once per distinct argument set and
+// replayed.  Large chunks (every kernel runs for >> a launch) and stats collection (events between stages) launch
+// directly.
+int run_chunk_graphed(bbme_ctx* c, Slot& s, int n, const uint8_t* d_in1, const uint8_t* d_in2, size_t in_pitch,
+                      size_t in_plane, float* d_flow, size_t flow_plane, int16_t* d_compact, size_t compact_plane,
+                      int factor = 1, bool seq = false) {
+  if (!c->use_graphs || c->opt.collect_stats || c->opt.keep_search_mv || n > 16)
+    return run_chunk(c, s, n, d_in1, d_in2, in_pitch, in_plane, d_flow, flow_plane, d_compact, compact_plane, factor, seq);
+  for (auto& g : s.graphs) {
+    if (g.n == n && g.factor == factor && g.seq == (int)seq && g.in1 == d_in1 && g.in2 == d_in2 && g.flow == d_flow &&
+        g.compact == d_compact && g.in_pitch == in_pitch && g.in_plane == in_plane && g.flow_plane == flow_plane &&
+        g.compact_plane == compact_plane) {
+      CUDA_TRY(c, cudaGraphLaunch(g.exec, s.stream));
+      c->launches += g.launches;
+      c->search_launches += g.search_launches;
+      return BBME_OK;
+    }
+  }
+  const uint32_t launches_before = c->launches, search_before = c->search_launches;
+  if (cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    return run_chunk(c, s, n, d_in1, d_in2, in_pitch, in_plane, d_flow, flow_plane, d_compact, compact_plane, factor, seq);
+  }
+  int rc = run_chunk(c, s, n, d_in1, d_in2, in_pitch, in_plane, d_flow, flow_plane, d_compact, compact_plane, factor, seq);
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(s.stream, &graph);
+  cudaGraphExec_t exec = nullptr;
+  if (rc == BBME_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&exec, graph, 0);
+  if (graph) cudaGraphDestroy(graph);
+  if (rc != BBME_OK) return rc;
+  if (e != cudaSuccess || !exec) {  // capture not possible here (e.g. a caller stream that is already capturing): launch directly
+    cudaGetLastError();
+    c->launches = launches_before;
+    c->search_launches = search_before;
+    return run_chunk(c, s, n, d_in1, d_in2, in_pitch, in_plane, d_flow, flow_plane, d_compact, compact_plane, factor, seq);
+  }
+  if (s.graphs.size() >= 8) {
+    cudaGraphExecDestroy(s.graphs.front().exec);
+    s.graphs.erase(s.graphs.begin());
+  }
+  s.graphs.push_back({n, factor, (int)seq, d_in1, d_in2, d_flow, d_compact, in_pitch, in_plane, flow_plane, compact_plane, exec,
+                      c->launches - launches_before, c->search_launches - search_before});
+  CUDA_TRY(c, cudaGraphLaunch(exec, s.stream));
+  return BBME_OK;
+}
+
 int collect_after_sync(bbme_ctx* c) {
   if (!c->opt.collect_stats || !c->stats_armed) return BBME_OK;
   for (Slot& s : c->slots) {
@@ -447,6 +507,7 @@ int bbme_create(bbme_ctx** out, int device) {
   bbme_ctx* c = new bbme_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
+  if (const char* g = getenv("BBME_GRAPHS")) c->use_graphs = atoi(g) != 0;
   if (const char* gr = getenv("BBME_GRID_ROUNDS")) {
     const int v = atoi(gr);
     if (v >= 0 && v <= 64) c->grid_rounds = v;
@@ -614,7 +675,7 @@ static int estimate_batch_async_impl(bbme_ctx* c, int n, int factor, const uint8
       CUDA_TRY(c, cudaMemcpy2DAsync(s.in2 + (size_t)i * in_plane, in_pitch, im2[start + i], pitch, w, h,
                                     cudaMemcpyHostToDevice, s.stream));
     }
-    int rc = run_chunk(c, s, m, s.in1, s.in2, in_pitch, in_plane, s.out, out_plane, nullptr, 0, factor);
+    int rc = run_chunk_graphed(c, s, m, s.in1, s.in2, in_pitch, in_plane, s.out, out_plane, nullptr, 0, factor);
     if (rc) return rc;
     for (int i = 0; i < m; ++i)
       CUDA_TRY(c, cudaMemcpyAsync(flow[start + i], s.out + (size_t)i * out_plane, flow_bytes, cudaMemcpyDeviceToHost, s.stream));
@@ -662,7 +723,7 @@ int bbme_estimate_sequence_async(bbme_ctx* c, int n_frames, const uint8_t* const
     for (int i = 0; i <= m; ++i)
       CUDA_TRY(c, cudaMemcpy2DAsync(s.in1 + (size_t)i * c->in_plane, c->in_pitch, frames[start + i], pitch, c->shape.width,
                                     c->shape.height, cudaMemcpyHostToDevice, s.stream));
-    int rc = run_chunk(c, s, m, s.in1, nullptr, c->in_pitch, c->in_plane, s.out, c->out_plane, nullptr, 0, 1, true);
+    int rc = run_chunk_graphed(c, s, m, s.in1, nullptr, c->in_pitch, c->in_plane, s.out, c->out_plane, nullptr, 0, 1, true);
     if (rc) return rc;
     for (int i = 0; i < m; ++i)
       CUDA_TRY(c, cudaMemcpyAsync(flow[start + i], s.out + (size_t)i * c->out_plane, flow_bytes, cudaMemcpyDeviceToHost, s.stream));
@@ -704,7 +765,7 @@ int bbme_estimate_sequence_device(bbme_ctx* c, int n_frames, const uint8_t* d_fr
                                       (size_t)c->shape.height, cudaMemcpyDeviceToDevice, s.stream));
       src = s.in1; sp = c->in_pitch; spl = c->in_plane;
     }
-    int rc = run_chunk(c, s, m, src, nullptr, sp, spl, d_flow + (size_t)start * flow_plane, flow_plane, nullptr, 0, 1, true);
+    int rc = run_chunk_graphed(c, s, m, src, nullptr, sp, spl, d_flow + (size_t)start * flow_plane, flow_plane, nullptr, 0, 1, true);
     if (rc) return rc;
   }
   return BBME_OK;
@@ -742,7 +803,7 @@ static int estimate_device_impl(bbme_ctx* c, int n, const uint8_t* d1, const uin
   for (int start = 0; start < n; start += chunk, ++ci) {
     Slot& s = c->slots[ci % c->slots.size()];
     const int m = (n - start < chunk) ? (n - start) : chunk;
-    int rc = run_chunk(c, s, m, d1 + (size_t)start * plane, d2 + (size_t)start * plane, pitch, plane,
+    int rc = run_chunk_graphed(c, s, m, d1 + (size_t)start * plane, d2 + (size_t)start * plane, pitch, plane,
                        d_flow ? d_flow + (size_t)start * flow_plane : nullptr, flow_plane,
                        d_mv ? d_mv + (size_t)start * mv_plane : nullptr, mv_plane, factor);
     if (rc) return rc;
