@@ -36,6 +36,27 @@ WORKLOAD = ("BASELINE config 4: batch of synthetic 1920x1080 8-bit luma frame pa
             "+-32 search = search_size 80, 3-level pyramid, 2 regularisation sweeps per block size), sharded by pair")
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Only the JSON line may reach stdout: libraries (NCCL prints its version there) get stderr instead."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -146,7 +167,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args, rank, local_rank, world):
@@ -381,7 +402,7 @@ def run_ours(args, rank, local_rank, world):
             "bit_exact_vs_oracle": parity, "gather_matches_local_fields": gather_ok,
             "wall_s_timed_region": t_wall,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -404,6 +425,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer arm")
     ap.add_argument("--no-check", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     rank = env_int("RANK", 0)
     local_rank = env_int("LOCAL_RANK", 0)
     world = env_int("WORLD_SIZE", 1)
