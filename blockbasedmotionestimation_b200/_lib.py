@@ -8,7 +8,7 @@ import os
 
 BBME_MAX_LEVELS = 16
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbbme.so")
+LIB_PATH = os.environ.get("BBME_LIB") or os.path.join(_HERE, "libbbme.so")  # BBME_LIB: tuning builds of the same library
 
 
 class BbmeShape(C.Structure):

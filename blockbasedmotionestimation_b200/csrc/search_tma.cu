@@ -30,8 +30,22 @@
 
 namespace bbme {
 
-constexpr int kStages = 3;
-constexpr int kConsumerWarps = 8;
+// CTA shape: one producer warp + kConsumerWarps consumer warps over a ring of kStages stages, kMinCtas CTAs per SM
+// (register cap = 64 K / (kMinCtas * kThreads)).  The macros exist for tuning experiments: one CTA of
+// 1 + 16 warps over a five-stage ring measured 71.6 % of the integer peak on config 2, two CTAs of 1 + 8 warps over
+// three stages each 68.8 %; 18-19 consumer warps or 6-8 stages change nothing, 20 warps spill.
+#ifndef BBME_STAGES
+#define BBME_STAGES 5
+#endif
+#ifndef BBME_CW
+#define BBME_CW 16
+#endif
+#ifndef BBME_MINB
+#define BBME_MINB 1
+#endif
+constexpr int kStages = BBME_STAGES;
+constexpr int kConsumerWarps = BBME_CW;
+constexpr int kMinCtas = BBME_MINB;
 constexpr int kThreads = 32 * (1 + kConsumerWarps);
 constexpr int kBlockSlots = kStages + 1;
 
@@ -129,7 +143,7 @@ __device__ __forceinline__ void spiral_unrank(uint32_t rank, int& dx, int& dy) {
 }
 
 template <int BS, int SEG, int PWW, bool K64>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, kMinCtas)
 k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant__ CUtensorMap map_blk,
              const TmaSearchArgs a) {
   constexpr int TW = BS >= 16 ? 16 : BS;   // tile width / height held in registers
@@ -524,7 +538,10 @@ static bool make_geom(int w, int h, int bs, int R, TmaGeom* g) {
   const int box_w = pww * 4;
   const int segs_total = (n + seg - 1) / seg;
   const int blk_bytes = bs * (bs >= 16 ? bs : 16);
-  const size_t budget = 24 * 1024;  // per stage
+  // per stage: 24 KB, or what the CTA's 200 KB leave per stage next to the spiral-rank table
+  const size_t rank_bytes = use_k64 ? 0 : (((size_t)(n + seg) * n * 2 + 127) / 128) * 128;
+  size_t budget = (200 * 1024 - rank_bytes) / kStages / 128 * 128;
+  if (budget > 24 * 1024) budget = 24 * 1024;
   int spb = segs_total;
   size_t one_box = 0;
   for (;;) {
@@ -559,6 +576,7 @@ static bool make_geom(int w, int h, int bs, int R, TmaGeom* g) {
   g->a.box1_off_words = two_box ? (int)(one_box / 4) : 0;
   g->a.rank_off = kStages * g->a.stage_bytes;
   g->smem = (size_t)g->a.rank_off + (use_k64 ? 0 : (((size_t)(n + seg) * n * 2 + 127) / 128) * 128);
+  if (g->smem > 200 * 1024) return false;  // ring + rank table must fit the CTA's shared memory: generic kernel instead
   return true;
 }
 
@@ -607,7 +625,7 @@ void launch_search_tma(const TmaSearchPlan& plan, ImgView i1, ImgView i2, MvView
   a.mv_plane = mv.plane;
   a.counters = counters;
   const int total = a.gw * a.gh * n;
-  int grid = sm_count * 2;
+  int grid = sm_count * kMinCtas;
   if (grid > total) grid = total;
 #define BBME_CASE(BS_, SEG_, PWW_) \
   if (!g.k64 && plan.bs == BS_ && plan.seg == SEG_ && a.pww == PWW_) { launch_inst<BS_, SEG_, PWW_, false>(plan, a, grid, s); return; }
