@@ -481,20 +481,23 @@ static int encode_u8_3d(CUtensorMap* map, const uint8_t* base, int w, int h, int
 }
 
 static int pick_seg(int bs, int R) {
-  // lane efficiency of the flattened (column, segment) item space; candidates: instantiated SEG values
+  // Candidate rows per lane.  Cost of a 32-lane work item per lane, in ALU-pipe instructions: the funnel shifts of
+  // SEG + T - 1 window rows, SEG * T * T/4 SADs, ~2 per candidate for the key, and a fixed part (item fetch, tile
+  // load, reductions) that weighs most on 8x8 blocks, whose items hold a quarter of the SADs of a 16x16 item.
+  // 16x16 / 32x32: 13 or 11 (17 and 22 were measured slower, with and without register spills); 8x8 blocks also get
+  // 26 and 43: config 3 (8x8, +-64) went from 42 % to 64 % of the integer peak with 43.
   const int n = 2 * R + 1;
-  const int cands[2] = {13, 11};
+  const int T = bs >= 16 ? 16 : bs;
+  const int cands[4] = {13, 11, 26, 43};
+  const int ncand = bs == 8 ? 4 : 2;
   int best = 13;
   double best_eff = -1.0;
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < ncand; ++i) {
     const int seg = cands[i];
     const int segs = (n + seg - 1) / seg;
-    const int items = n * segs;
-    const int wi = (items + 31) / 32;
-    // useful SADs / issued SADs, discounted by the per-item row overhead (SEG + T - 1 rows of loads)
-    const int T = bs >= 16 ? 16 : bs;
-    double eff = (double)(n * n) / ((double)wi * 32.0 * seg);
-    eff *= (double)seg / (double)(seg + 0.06 * (seg + T - 1));
+    const int wi = (n * segs + 31) / 32;
+    const double per_lane = (seg + T - 1) * (T / 4 + 0.2) + (double)seg * T * (T / 4) + 2.0 * seg + 200.0;
+    const double eff = (double)n * n * T * (T / 4) / ((double)wi * 32.0 * per_lane);
     if (eff > best_eff) { best_eff = eff; best = seg; }
   }
   return best;
@@ -634,7 +637,7 @@ void launch_search_tma(const TmaSearchPlan& plan, ImgView i1, ImgView i2, MvView
 #define BBME_CASES(BS_, SEG_) \
   BBME_CASE(BS_, SEG_, 16) BBME_CASE(BS_, SEG_, 24) BBME_CASE(BS_, SEG_, 32) BBME_CASE(BS_, SEG_, 40) \
   BBME_CASE(BS_, SEG_, 48) BBME_CASE(BS_, SEG_, 64)
-  BBME_CASES(8, 13) BBME_CASES(8, 11) BBME_CASES(16, 13) BBME_CASES(16, 11) BBME_CASES(32, 13) BBME_CASES(32, 11)
+  BBME_CASES(8, 13) BBME_CASES(8, 11) BBME_CASES(8, 26) BBME_CASES(8, 43) BBME_CASES(16, 13) BBME_CASES(16, 11) BBME_CASES(32, 13) BBME_CASES(32, 11)
   BBME_CASE64(16, 13, 40) BBME_CASE64(16, 13, 64) BBME_CASE64(16, 11, 40) BBME_CASE64(16, 11, 64)
   BBME_CASE64(32, 13, 40) BBME_CASE64(32, 13, 64) BBME_CASE64(32, 11, 40) BBME_CASE64(32, 11, 64)
 #undef BBME_CASE64
