@@ -597,8 +597,8 @@ __device__ __forceinline__ short2 reg_eval_small(const RegArgs& a, int pair, con
 
 // Blocks of 8x8 and larger are evaluated by a TEAM of adjacent lanes (8 for 8x8, 16 for 16x16, 32 above): a lane
 // takes one block row (32x32 and larger: bs/32 rows, 16 bytes at a time), loads its slice of all nine candidate
-// windows at once, and the partial SADs are combined with xor-shuffles inside the team; every lane of the team ends
-// up with the same nine energies and the same winner.
+// windows at once; the partial SADs are reduce-scattered inside the team so that lane i holds candidate i's SAD, computes
+// that candidate's smoothness and energy, and a shuffle argmin leaves every lane of the team with the same winner.
 template <int TEAM>
 __device__ __forceinline__ short2 reg_eval_team(const RegArgs& a, int pair, const short2* __restrict__ O,
                                                 const short2* P, int bx, int by, int tl, uint32_t team_mask) {
@@ -633,24 +633,33 @@ __device__ __forceinline__ short2 reg_eval_team(const RegArgs& a, int pair, cons
     inb |= ok ? (1u << i) : 0u;
     bp[i] = ref + (size_t)(ok ? py : y) * pitch + (ok ? px : x);
   }
-  uint32_t sad[9];
+  // Partial SADs of this lane's rows.  A window row starts at any byte: it is fetched as the two aligned 16-byte (8x8
+  // blocks: 8-byte) vectors that contain it -- two requests per row instead of five (three) 32-bit ones; a team's lanes
+  // read 16 different rows, i.e. 16 cache lines per request, and the L1's line rate, not its bandwidth, bounded these
+  // kernels -- and the wanted words are selected by the start offset's word index before the byte shift.
+  uint32_t v[16];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) sad[i] = 0u;
+  for (int i = 0; i < 16; ++i) v[i] = 0u;
   if (TEAM == 8) {
     const size_t ro = (size_t)tl * pitch;
     const uint2 A = __ldg(reinterpret_cast<const uint2*>(blk + ro));
-    uint32_t wv[9][3], sh[9];
+    uint2 q0[9], q1[9];
+    uint32_t off[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
       const uintptr_t ab = reinterpret_cast<uintptr_t>(bp[i] + ro);
-      const uint32_t* bw = reinterpret_cast<const uint32_t*>(ab & ~(uintptr_t)3);
-      sh[i] = (uint32_t)(ab & 3) * 8u;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) wv[i][k] = __ldg(bw + k);
+      const uint2* q = reinterpret_cast<const uint2*>(ab & ~(uintptr_t)7);
+      off[i] = (uint32_t)(ab & 7);
+      q0[i] = __ldg(q);
+      q1[i] = __ldg(q + 1);
     }
 #pragma unroll
-    for (int i = 0; i < 9; ++i)
-      sad[i] = sad4(A.y, __funnelshift_r(wv[i][1], wv[i][2], sh[i]), sad4(A.x, __funnelshift_r(wv[i][0], wv[i][1], sh[i]), 0u));
+    for (int i = 0; i < 9; ++i) {
+      const bool w1 = (off[i] & 4u) != 0u;
+      const uint32_t sh = (off[i] & 3u) * 8u;
+      const uint32_t a0 = w1 ? q0[i].y : q0[i].x, a1 = w1 ? q1[i].x : q0[i].y, a2 = w1 ? q1[i].y : q1[i].x;
+      v[i] = sad4(A.y, __funnelshift_r(a1, a2, sh), sad4(A.x, __funnelshift_r(a0, a1, sh), 0u));
+    }
   } else {
     // 16 bytes of one row per step; TEAM == 16: one step, TEAM == 32: (bs / 32) rows x (bs / 16) column chunks
     const int rows = TEAM == 16 ? 1 : bs / 32;
@@ -659,79 +668,110 @@ __device__ __forceinline__ short2 reg_eval_team(const RegArgs& a, int pair, cons
       for (int ch = 0; ch < chunks; ++ch) {
         const size_t ro = (size_t)(rr * TEAM + tl) * pitch + ch * 16;
         const uint4 A = __ldg(reinterpret_cast<const uint4*>(blk + ro));
-        uint32_t wv[9][5], sh[9];
+        uint4 q0[9], q1[9];
+        uint32_t off[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
           const uintptr_t ab = reinterpret_cast<uintptr_t>(bp[i] + ro);
-          const uint32_t* bw = reinterpret_cast<const uint32_t*>(ab & ~(uintptr_t)3);
-          sh[i] = (uint32_t)(ab & 3) * 8u;
-#pragma unroll
-          for (int k = 0; k < 5; ++k) wv[i][k] = __ldg(bw + k);
+          const uint4* q = reinterpret_cast<const uint4*>(ab & ~(uintptr_t)15);
+          off[i] = (uint32_t)(ab & 15);
+          q0[i] = __ldg(q);
+          q1[i] = __ldg(q + 1);
         }
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
-          uint32_t s = sad[i];
-          s = sad4(A.x, __funnelshift_r(wv[i][0], wv[i][1], sh[i]), s);
-          s = sad4(A.y, __funnelshift_r(wv[i][1], wv[i][2], sh[i]), s);
-          s = sad4(A.z, __funnelshift_r(wv[i][2], wv[i][3], sh[i]), s);
-          s = sad4(A.w, __funnelshift_r(wv[i][3], wv[i][4], sh[i]), s);
-          sad[i] = s;
+          const bool s2 = (off[i] & 8u) != 0u, s1 = (off[i] & 4u) != 0u;
+          const uint32_t sh = (off[i] & 3u) * 8u;
+          // words 0..7 of the 32 aligned bytes; skip two words, then one
+          const uint32_t t0 = s2 ? q0[i].z : q0[i].x, t1 = s2 ? q0[i].w : q0[i].y, t2 = s2 ? q1[i].x : q0[i].z,
+                         t3 = s2 ? q1[i].y : q0[i].w, t4 = s2 ? q1[i].z : q1[i].x, t5 = s2 ? q1[i].w : q1[i].y;
+          const uint32_t a0 = s1 ? t1 : t0, a1 = s1 ? t2 : t1, a2 = s1 ? t3 : t2, a3 = s1 ? t4 : t3, a4 = s1 ? t5 : t4;
+          uint32_t sum = v[i];
+          sum = sad4(A.x, __funnelshift_r(a0, a1, sh), sum);
+          sum = sad4(A.y, __funnelshift_r(a1, a2, sh), sum);
+          sum = sad4(A.z, __funnelshift_r(a2, a3, sh), sum);
+          sum = sad4(A.w, __funnelshift_r(a3, a4, sh), sum);
+          v[i] = sum;
         }
       }
     }
   }
 
-  // smoothness: S_i = sum over gathered candidates k of |c_k.x - c_i.x| + |c_k.y - c_i.y|  (:637-641), computed while the
-  // window loads are in flight.  Accumulated in float like the reference (integer-valued, < 2^24, exact): FADD with |.|
-  // source modifiers runs on the FMA pipe, which is idle here, while the integer form loaded the ALU pipe that the SADs,
-  // funnel shifts and shuffles need.  All nine slots are summed, then the missing slots' share is removed (each holds a
-  // copy of C, i.e. contributes d(i, 0)).
-  float fx[9], fy[9], S[9];
+  // Reduce-scatter inside the team: the nine sums live in 16 slots; at each step a lane keeps one half of its slots and
+  // hands the other half to its partner, so that lane i (8x8 teams: lane i / 2) ends with the team total of candidate i
+  // -- 15 (14) shuffles instead of 9 * log2(TEAM).  32-lane teams first fold their two halves together.
+  if (TEAM == 32) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) v[i] += __shfl_xor_sync(team_mask, v[i], 16);
+  }
+  constexpr int W = TEAM >= 16 ? 16 : 8;  // lanes the slots are scattered over
+  constexpr int NS = 16 / W;              // slots a lane ends up with
+#pragma unroll
+  for (int off = W / 2, n = 8; off >= 1; off >>= 1, n >>= 1) {
+    const bool upper = (tl & off) != 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < n) {
+        const uint32_t lo = v[j], hi = v[j + n];
+        const uint32_t recv = __shfl_xor_sync(team_mask, upper ? lo : hi, off);
+        v[j] = (upper ? hi : lo) + recv;
+      }
+    }
+  }
+  const int cid0 = W == 16 ? (tl & 15) : 2 * (tl & 7);  // candidate of this lane's slot 0 (the reduce-scatter's bit order)
+
+  // Each lane finishes ITS candidate(s): smoothness S_i = sum over the gathered candidates k of |c_k.x - c_i.x| +
+  // |c_k.y - c_i.y| (:637-641) in float like the reference (integer-valued, < 2^24, exact; FADD with |.| modifiers on the
+  // FMA pipe); all nine slots are summed and the missing slots' share removed (each holds a copy of C, i.e. d(i, 0)).
+  // Before, every lane of a team repeated all 36 pair distances.
+  uint32_t pk[9];
+  float fx[9], fy[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) {
+    pk[i] = pack_mv(c[i]);
     fx[i] = (float)c[i].x;
     fy[i] = (float)c[i].y;
-    S[i] = 0.f;
   }
+  const float n_missing = (float)(9 - __popc(vmask));
+  float best_e = FLT_MAX;
+  int best_i = 15;
 #pragma unroll
-  for (int i = 0; i < 9; ++i) {
+  for (int sidx = 0; sidx < NS; ++sidx) {
+    const int i = cid0 + sidx;
+    float mx = fx[0], my = fy[0];
 #pragma unroll
-    for (int k = i + 1; k < 9; ++k) {
-      const float d = __fadd_rn(fabsf(__fsub_rn(fx[i], fx[k])), fabsf(__fsub_rn(fy[i], fy[k])));
-      S[i] = __fadd_rn(S[i], d);
-      S[k] = __fadd_rn(S[k], d);
+    for (int q = 1; q < 9; ++q) {
+      mx = (i == q) ? fx[q] : mx;
+      my = (i == q) ? fy[q] : my;
     }
+    float S = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) S = __fadd_rn(S, __fadd_rn(fabsf(__fsub_rn(mx, fx[k])), fabsf(__fsub_rn(my, fy[k]))));
+    const float d0 = __fadd_rn(fabsf(__fsub_rn(mx, fx[0])), fabsf(__fsub_rn(my, fy[0])));
+    S = __fmaf_rn(-n_missing, d0, S);
+    const bool valid = i < 9 && ((vmask >> i) & 1u);
+    const bool in_image = ((inb >> i) & 1u) != 0u;
+    // (:607) un-fused, (:578-582) FLT_MAX outside the image; slots without a neighbour can never win
+    const float e = (valid && in_image) ? __fadd_rn(__uint2float_rn(v[sidx]), __fmul_rn(a.lm, S)) : FLT_MAX;
+    const int ii = valid ? i : 15;
+    const bool take = e < best_e || (e == best_e && ii < best_i);
+    best_e = take ? e : best_e;
+    best_i = take ? ii : best_i;
   }
-  {
-    const float n_missing = (float)(9 - __popc(vmask));
+  // argmin over the team: smallest energy, ties to the smallest index == the reference's scan with strict '<' from
+  // index 1 (:653-659); index 0 (C) is always present, so an all-FLT_MAX block keeps its vector
 #pragma unroll
-    for (int i = 1; i < 9; ++i) {
-      const float d0 = __fadd_rn(fabsf(__fsub_rn(fx[i], fx[0])), fabsf(__fsub_rn(fy[i], fy[0])));
-      S[i] = __fmaf_rn(-n_missing, d0, S[i]);
-    }
+  for (int off = W / 2; off >= 1; off >>= 1) {
+    const float oe = __shfl_xor_sync(team_mask, best_e, off);
+    const int oi = __shfl_xor_sync(team_mask, best_i, off);
+    const bool take = oe < best_e || (oe == best_e && oi < best_i);
+    best_e = take ? oe : best_e;
+    best_i = take ? oi : best_i;
   }
+  uint32_t r = pk[0];
 #pragma unroll
-  for (int off = TEAM / 2; off > 0; off >>= 1) {
-#pragma unroll
-    for (int i = 0; i < 9; ++i) sad[i] += __shfl_xor_sync(team_mask, sad[i], off);
-  }
-  float best = 0.f;
-  int best_i = 0;
-#pragma unroll
-  for (int i = 0; i < 9; ++i) {
-    const float e = ((inb >> i) & 1u) ? __fadd_rn(__uint2float_rn(sad[i]), __fmul_rn(a.lm, S[i])) : FLT_MAX;
-    if (i == 0) {
-      best = e;
-    } else {
-      const bool take = ((vmask >> i) & 1u) && (e < best);  // strict '<' from index 1 (:653-659)
-      best = take ? e : best;
-      best_i = take ? i : best_i;
-    }
-  }
-  short2 r = c0;
-#pragma unroll
-  for (int i = 1; i < 9; ++i) r = (best_i == i) ? c[i] : r;
-  return r;
+  for (int i = 1; i < 9; ++i) r = (best_i == i) ? pk[i] : r;
+  return make_short2((short)(r & 0xffffu), (short)(r >> 16));
 }
 
 // TEAM == 1 evaluates 2x2 blocks, TEAM == 2 is the tag for "one thread per 4x4 block" (TEAMSZ below is 1 for both)
