@@ -304,7 +304,7 @@ def run_ours(args, rank, local_rank, world):
     alg_bytes_pair = 2 * WIDTH * HEIGHT + 8 * Wp * Hp
     roofline = {
         "bound": "int",  # integer SIMD (VABSDIFF4) issue rate; HBM time is ~50x smaller (see roofline_hbm)
-        "kernel": "k_search_tma<16,13> (all pyramid levels)",
+        "kernel": "k_search_tma<16,13,24> (all pyramid levels)",
         "achieved": achieved / 1e9, "peak": peak_absdiff / 1e9, "unit": "G absdiff/s",
         "frac": (achieved / peak_absdiff) if peak_absdiff > 0 else None,
         "peak_source": f"live VABSDIFF4.U8.ACC issue-rate micro-benchmark on this GPU at {peak_mhz:.0f} MHz "
@@ -312,9 +312,9 @@ def run_ours(args, rank, local_rank, world):
         "algorithmic_absdiffs_per_launch": absdiffs / n_search,
         "avg_launch_ms": ms_search / n_search, "launches_per_step": n_search,
         # dram__bytes_read.sum + dram__bytes_write.sum of the level-0 launch (128 pairs) from the committed ncu capture
-        # profiles/r01b_search_l0_ncu.txt (not re-measured here); algorithmic bytes of that launch: 2 frames x 2.09 MB x 128
-        "traffic": 862.3e6 if P == 128 else None,
-        "traffic_note": "bytes per level-0 launch of 128 pairs (ncu --set full, profiles/r01b_search_l0_ncu.txt); algorithmic 535 MB + 4 MB of vectors",
+        # profiles/r01c_search_l0_ncu.txt (not re-measured here); algorithmic bytes of that launch: 2 frames x 2.09 MB x 128
+        "traffic": 566.6e6 if P == 128 else None,
+        "traffic_note": "bytes per level-0 launch of 128 pairs (ncu --set full, profiles/r01c_search_l0_ncu.txt); algorithmic 535 MB + 4 MB of vectors",
     }
     roofline_hbm = {
         "bound": "hbm", "algorithmic_bytes_per_pair": alg_bytes_pair,
