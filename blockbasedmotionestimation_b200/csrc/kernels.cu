@@ -210,41 +210,49 @@ __global__ void __launch_bounds__(128) k_pyrdown(ImgView s1, ImgView s2, uint8_t
   const int sw = sv.w, sh = sv.h;
   const bool live = 8 * t < dw;            // whole warps stay alive for the shuffles
   const bool full = 16 * t + 16 <= sv.pitch;
-  int acc[8];
+  // Output i of the strip is the 5x5 window centred on source pixel 16t + 2i.  The taps stay packed: a window row is
+  // four bytes of one (half-word shifted) source word times (1,4,6,4) plus one byte of the next word, i.e. two
+  // byte-dot-products (IDP.4A) that accumulate straight into acc[i]; the vertical weight of the row is folded into the
+  // dot-product constants (6 * 6 = 36 fits a byte).  100 instructions per strip instead of ~300 with unpacked pixels --
+  // the kernel was bound by the ALU pipe, not by HBM.
+  uint32_t acc[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0;
+  for (int i = 0; i < 8; ++i) acc[i] = 0u;
 #pragma unroll
   for (int j = 0; j < 5; ++j) {
-    const int wj = (j == 0 || j == 4) ? 1 : ((j == 2) ? 6 : 4);
+    const uint32_t wj = (j == 0 || j == 4) ? 1u : ((j == 2) ? 6u : 4u);
+    const uint32_t k4 = wj * 0x04060401u;  // bytes (b0..b3) x (1,4,6,4)
+    const uint32_t k_b2 = wj << 16;        // byte 2 x 1
+    const uint32_t k_b0 = wj;              // byte 0 x 1
     const uint8_t* row = src + (size_t)reflect101(2 * y + j - 2, sh) * sv.pitch;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (live && full) v = __ldg(reinterpret_cast<const uint4*>(row + 16 * t));
     // halo: bytes 16t-2, 16t-1 (high half of the left neighbour's last word) and 16t+16 (right neighbour's first byte)
-    uint32_t left = __shfl_up_sync(0xffffffffu, v.w, 1);
-    uint32_t right = __shfl_down_sync(0xffffffffu, v.x, 1);
-    int p[19];  // source pixels 16t-2 .. 16t+16
+    uint32_t L = __shfl_up_sync(0xffffffffu, v.w, 1);
+    uint32_t R = __shfl_down_sync(0xffffffffu, v.x, 1);
     if (live) {
-      if (lane == 0 || t == 0) {
-        p[0] = (int)__ldg(row + reflect101(16 * t - 2, sw));
-        p[1] = (int)__ldg(row + reflect101(16 * t - 1, sw));
-      } else {
-        p[0] = (int)((left >> 16) & 0xffu);
-        p[1] = (int)(left >> 24);
-      }
-      if (lane == 31 || 16 * t + 16 >= sw) p[18] = (int)__ldg(row + reflect101(16 * t + 16, sw));
-      else p[18] = (int)(right & 0xffu);
-      const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int q = 0; q < 16; ++q) p[2 + q] = (int)((wd[q >> 2] >> ((q & 3) * 8)) & 0xffu);
+      if (lane == 0 || t == 0)
+        L = ((uint32_t)__ldg(row + reflect101(16 * t - 2, sw)) << 16) | ((uint32_t)__ldg(row + reflect101(16 * t - 1, sw)) << 24);
+      if (lane == 31 || 16 * t + 16 >= sw) R = (uint32_t)__ldg(row + reflect101(16 * t + 16, sw));
+      uint32_t w[6] = {L, v.x, v.y, v.z, v.w, R};
       if (16 * t + 16 > sw || !full) {  // ragged right edge: pixels past the image width are reflected, not read from the pitch tail
 #pragma unroll
-        for (int q = 0; q < 16; ++q)
-          if (16 * t + q >= sw || !full) p[2 + q] = (int)__ldg(row + reflect101(16 * t + q, sw));
+        for (int q = 0; q < 16; ++q) {
+          if (16 * t + q >= sw || !full) {
+            const uint32_t px = (uint32_t)__ldg(row + reflect101(16 * t + q, sw));
+            w[1 + (q >> 2)] = (w[1 + (q >> 2)] & ~(0xffu << ((q & 3) * 8))) | (px << ((q & 3) * 8));
+          }
+        }
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int hsum = p[2 * i] + 4 * p[2 * i + 1] + 6 * p[2 * i + 2] + 4 * p[2 * i + 3] + p[2 * i + 4];
-        acc[i] += wj * hsum;
+      for (int m = 0; m < 4; ++m) {
+        // even output 2m: pixels 16t+4m-2 .. 16t+4m+2 = (w[m].b2, w[m].b3, w[m+1].b0, w[m+1].b1), w[m+1].b2
+        const uint32_t x = __funnelshift_r(w[m], w[m + 1], 16);
+        acc[2 * m] = __dp4a(x, k4, acc[2 * m]);
+        acc[2 * m] = __dp4a(w[m + 1], k_b2, acc[2 * m]);
+        // odd output 2m+1: pixels 16t+4m .. 16t+4m+4 = w[m+1].b0..b3, w[m+2].b0
+        acc[2 * m + 1] = __dp4a(w[m + 1], k4, acc[2 * m + 1]);
+        acc[2 * m + 1] = __dp4a(w[m + 2], k_b0, acc[2 * m + 1]);
       }
     }
   }
@@ -253,8 +261,8 @@ __global__ void __launch_bounds__(128) k_pyrdown(ImgView s1, ImgView s2, uint8_t
   uint32_t lo = 0, hi = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    lo |= (uint32_t)((acc[i] + 128) >> 8) << (8 * i);
-    hi |= (uint32_t)((acc[4 + i] + 128) >> 8) << (8 * i);
+    lo |= ((acc[i] + 128u) >> 8) << (8 * i);
+    hi |= ((acc[4 + i] + 128u) >> 8) << (8 * i);
   }
   if (8 * t + 8 <= dw) {
     *reinterpret_cast<uint2*>(dst) = make_uint2(lo, hi);
@@ -834,16 +842,16 @@ __device__ __forceinline__ void push_dependents(bool changed, int bx, int by, in
 //  k_reg_eval      evaluation of the listed blocks by a fixed-size grid that strides over the list; blocks whose
 //                  value changed enqueue their dependents (they may have used a stale "pred" value) for the rounds.
 __global__ void __launch_bounds__(256) k_reg_classify4(RegArgs a) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int pair = blockIdx.y;
+  // block = 64 x 4 threads: 64 four-block groups along a row, four rows (no integer division per thread)
+  const int tx = blockIdx.x * 64 + threadIdx.x, by = blockIdx.y * 4 + threadIdx.y;
+  const int pair = blockIdx.z;
   const int gw = a.gw, gh = a.gh, gw4 = gw >> 2;
   const int lane = threadIdx.x & 31;
-  const bool live = t < gw4 * gh;
+  const bool live = tx < gw4 && by < gh;
   const uint32_t* __restrict__ O = reinterpret_cast<const uint32_t*>(a.O + (size_t)pair * a.mv_plane);
   uint32_t work = 0;
   int i0 = 0;
   if (live) {
-    const int tx = t % gw4, by = t / gw4;
     const int bx = tx * 4;
     i0 = by * gw + bx;
     // clamped coordinates: a clamped neighbour is the block itself or another neighbour, so the test is unchanged
@@ -1057,7 +1065,8 @@ void launch_reg_full(const RegArgs& a, int n, cudaStream_t s) {
   const int team = team_for(a.bs);
   const int lanes = team <= 2 ? 1 : team;
   const size_t nb = (size_t)a.gw * a.gh;
-  if ((a.gw & 3) == 0 && (a.mv_plane & 3) == 0) k_reg_classify4<<<dim3((unsigned)((nb / 4 + 255) / 256), n), 256, 0, s>>>(a);
+  if ((a.gw & 3) == 0 && (a.mv_plane & 3) == 0 && a.gh <= 4 * 65535)
+    k_reg_classify4<<<dim3((unsigned)((a.gw / 4 + 63) / 64), (unsigned)((a.gh + 3) / 4), n), dim3(64, 4), 0, s>>>(a);
   else k_reg_classify<<<dim3((unsigned)((nb + 255) / 256), n), 256, 0, s>>>(a);
   // a fixed-size grid strides over each pair's list (its length is only known on the device): enough CTAs to fill the
   // chip a few times over, never more than the list could need
