@@ -85,6 +85,7 @@ SIGNATURES = {
     "bbme_flo_read": (_I, [C.c_char_p, _P, _I, _I]),
     "bbme_flo_write": (_I, [C.c_char_p, _P, _I, _I]),
     "bbme_flow_aee": (C.c_double, [_P, _P, _I, _I]),
+    "bbme_flow_to_color": (_I, [_P, _I, _I, C.c_float, _P, _P]),
     "bbme_flow_strip_subsample": (_I, [_P, C.POINTER(BbmeShape), _I, _P]),
 }
 

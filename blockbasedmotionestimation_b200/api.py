@@ -406,6 +406,18 @@ class Flow:
         h, w, _ = gt.shape
         return float(self._lib.bbme_flow_aee(gt.ctypes.data, fl.ctypes.data, w, h))
 
+    def MotionToColor(self, input_img, maxmotion=-1.0):
+        """Flow::MotionToColor (rw_flow.cpp:202-249): (h, w, 2) float32 field -> (h, w, 3) uint8 image in OpenCV's BGR order."""
+        f = np.ascontiguousarray(input_img, np.float32)
+        h, w = f.shape[:2]
+        out = np.empty((h, w, 3), np.uint8)
+        rng = (C.c_float * 5)()
+        rc = self._lib.bbme_flow_to_color(f.ctypes.data, w, h, C.c_float(maxmotion), out.ctypes.data, rng)
+        if rc != 0:
+            raise BbmeError(rc, "bbme_flow_to_color")
+        self.last_motion_range = tuple(rng)
+        return out
+
     def StripAndSubsample(self, padded_flow, shape, factor):
         """main()'s post-processing (main_class.cpp:58-70)."""
         sh = BbmeShape()

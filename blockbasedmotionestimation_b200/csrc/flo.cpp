@@ -117,3 +117,70 @@ int bbme_flow_strip_subsample(const float* padded, const bbme_shape* sh, int fac
 }
 
 }  // extern "C"
+
+// Flow::MotionToColor + computeColor + makecolorwheel (rw_flow.cpp:202-300): Middlebury colour coding of a flow field.
+// Host code like the .flo codec (the reference writes flow.png from it, main_class.cpp:73-75).  The arithmetic follows
+// the reference expression by expression -- float sqrt / atan2 / division by the reference's FLOAT pi
+// (rw_flow.cpp:36), double only in `col *= .75` and `255.0 * col` -- so on the same libm the bytes are identical
+// (the tests compare with the reference's own function, compiled from the reference tree).
+namespace {
+struct ColorWheel {
+  int n = 0;
+  int c[60][3];  // MAXCOLS, rw_flow.h:5
+  void set(int r, int g, int b, int k) { c[k][0] = r; c[k][1] = g; c[k][2] = b; }
+  ColorWheel() {  // makecolorwheel, rw_flow.cpp:276-300
+    const int RY = 15, YG = 6, GC = 4, CB = 11, BM = 13, MR = 6;
+    int k = 0;
+    for (int i = 0; i < RY; i++) set(255, 255 * i / RY, 0, k++);
+    for (int i = 0; i < YG; i++) set(255 - 255 * i / YG, 255, 0, k++);
+    for (int i = 0; i < GC; i++) set(0, 255, 255 * i / GC, k++);
+    for (int i = 0; i < CB; i++) set(0, 255 - 255 * i / CB, 255, k++);
+    for (int i = 0; i < BM; i++) set(255 * i / BM, 0, 255, k++);
+    for (int i = 0; i < MR; i++) set(255, 0, 255 - 255 * i / MR, k++);
+    n = k;
+  }
+};
+
+}  // namespace
+
+extern "C" int bbme_flow_to_color(const float* flow, int width, int height, float maxmotion, uint8_t* bgr, float* range5) {
+  if (!flow || !bgr || width < 1 || height < 1) return BBME_E_ARG;
+  static const ColorWheel wheel;
+  const float kPi = 3.14159265358979323846f;  // the reference redefines M_PI as a float literal (rw_flow.cpp:36)
+  float maxx = -999, maxy = -999, minx = 999, miny = 999, maxrad = -1;  // rw_flow.cpp:205-207
+  const size_t n = (size_t)width * height;
+  for (size_t i = 0; i < n; ++i) {
+    const float fx = flow[2 * i], fy = flow[2 * i + 1];
+    if (unknown_flow(fx, fy)) continue;
+    maxx = maxx > fx ? maxx : fx;
+    maxy = maxy > fy ? maxy : fy;
+    minx = minx < fx ? minx : fx;
+    miny = miny < fy ? miny : fy;
+    const float rad = sqrtf(fx * fx + fy * fy);
+    maxrad = maxrad > rad ? maxrad : rad;
+  }
+  if (range5) { range5[0] = maxrad; range5[1] = minx; range5[2] = maxx; range5[3] = miny; range5[4] = maxy; }
+  if (maxmotion > 0) maxrad = maxmotion;  // :225-226
+  if (maxrad == 0) maxrad = 1;            // :228-229
+  for (size_t i = 0; i < n; ++i) {
+    uint8_t* pix = bgr + 3 * i;
+    const float u = flow[2 * i], v = flow[2 * i + 1];
+    if (unknown_flow(u, v)) { pix[0] = pix[1] = pix[2] = 0; continue; }
+    const float fx = u / maxrad, fy = v / maxrad;  // :245
+    const float rad = sqrtf(fx * fx + fy * fy);
+    const float a = atan2f(-fy, -fx) / kPi;
+    const float fk = (a + 1.0f) / 2.0f * (wheel.n - 1);
+    const int k0 = (int)fk;
+    const int k1 = (k0 + 1) % wheel.n;
+    const float f = fk - k0;
+    for (int b = 0; b < 3; b++) {
+      const float col0 = wheel.c[k0][b] / 255.0f;
+      const float col1 = wheel.c[k1][b] / 255.0f;
+      float col = (1 - f) * col0 + f * col1;
+      if (rad <= 1) col = 1 - rad * (1 - col);  // increase saturation with radius
+      else col *= .75;                          // out of range
+      pix[2 - b] = (uint8_t)(int)(255.0 * col);
+    }
+  }
+  return BBME_OK;
+}

@@ -211,6 +211,11 @@ int bbme_flo_read(const char* path, float* data, int width, int height);        
 int bbme_flo_write(const char* path, const float* data, int width, int height);   /* Flow::WriteFlowFile */
 /* Flow::CalculateMSE: average endpoint error over gt-known pixels (rw_flow.cpp:309-332). */
 double bbme_flow_aee(const float* gt, const float* flow, int width, int height);
+/* Flow::MotionToColor (rw_flow.cpp:202-274): Middlebury colour coding.  bgr: height x width x 3 bytes in OpenCV's
+ * channel order (what main() writes to flow.png, main_class.cpp:73-75); unknown vectors (|u| or |v| > 1e9, NaN) are
+ * black.  maxmotion <= 0: normalise by the largest known vector, like main() does (-1).  range5 (may be NULL) receives
+ * {max radius, min u, max u, min v, max v} over the known vectors -- the line the reference prints. */
+int bbme_flow_to_color(const float* flow, int width, int height, float maxmotion, uint8_t* bgr, float* range5);
 /* main()'s post-processing (main_class.cpp:58-70): strip padding, keep every `factor`-th pixel, divide by factor.
  * out: (height/factor) x (width/factor) x 2 with width/height the ORIGINAL (pre-padding) size. */
 int bbme_flow_strip_subsample(const float* padded_flow, const bbme_shape* shape, int factor, float* out);

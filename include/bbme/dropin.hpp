@@ -3,7 +3,7 @@
 //   class MF             <- motion_framework.h:9-54   (constructor :12, calcMotionBlockMatching :13, public ints :16-19)
 //   class PyramidLevel   <- pyramid_level.h:7-16
 //   class BlockPosition  <- block_position.h:4-9
-//   class Flow           <- rw_flow.h:9-38            (ReadFlowFile, WriteFlowFile, CalculateMSE)
+//   class Flow           <- rw_flow.h:9-38            (ReadFlowFile, WriteFlowFile, MotionToColor, CalculateMSE)
 //
 // Header-only: an application that used the reference's classes includes "motion_framework.h" / "rw_flow.h" from this
 // include/ directory instead of the reference's, links libbbme.so, and keeps its source unchanged.  What differs:
@@ -21,6 +21,7 @@
 #include "cvmat_min.hpp"
 #endif
 
+#include <cstdio>
 #include <cstdlib>
 #include <iostream>
 #include <stdexcept>
@@ -139,6 +140,16 @@ class Flow {
     const int rc = bbme_flo_write(filename, reinterpret_cast<const float*>(dense.data), dense.cols, dense.rows);
     if (rc == BBME_E_FORMAT) bbme_dropin::fatal("WriteFlowFile: filename should have extension '.flo'");
     if (rc != BBME_OK) bbme_dropin::fatal("WriteFlowFile: could not open file or problem writing data");
+  }
+  // Color code motion vectors for easier visualization (rw_flow.cpp:202-249); prints the reference's range line
+  void MotionToColor(cv::Mat& input_img, cv::Mat& output_img, float maxmotion) {
+    cv::Mat dense = (input_img.step == static_cast<size_t>(input_img.cols) * 8) ? input_img : input_img.clone();
+    output_img = cv::Mat::zeros(dense.rows, dense.cols, CV_8UC3);
+    float r[5];
+    const int rc = bbme_flow_to_color(reinterpret_cast<const float*>(dense.data), dense.cols, dense.rows, maxmotion,
+                                      output_img.data, r);
+    if (rc != BBME_OK) bbme_dropin::fatal("MotionToColor: bad arguments");
+    std::printf("max motion: %.4f  motion range: u = %.3f .. %.3f;  v = %.3f .. %.3f\n", r[0], r[1], r[2], r[3], r[4]);
   }
   // average endpoint error against the ground truth, unknown pixels skipped (rw_flow.cpp:309-332)
   double CalculateMSE(cv::Mat& gtruth, cv::Mat& flow) {

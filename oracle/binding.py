@@ -276,6 +276,7 @@ def load_ref():
         lib.ref_flow_write.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int]
         lib.ref_flow_mse.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         lib.ref_flow_mse.restype = C.c_double
+        lib.ref_flow_color.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]
         _ref = lib
     return _ref
 
@@ -299,3 +300,17 @@ def ref_estimate(im1, im2, search_size, block_size):
     if rc != 0:
         raise ValueError(f"ref_mf_run failed: {rc}")
     return flow, list(dims), tc.value, tr.value
+
+
+def ref_flow_color(flow, maxmotion=-1.0):
+    """The reference's own Flow::MotionToColor (oracle/_ref); None when oracle/_ref is not built."""
+    lib = load_ref()
+    if lib is None:
+        return None
+    flow = np.ascontiguousarray(flow, np.float32)
+    h, w = flow.shape[:2]
+    out = np.zeros((h, w, 3), np.uint8)
+    rc = lib.ref_flow_color(flow.ctypes.data, w, h, C.c_float(maxmotion), out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("ref_flow_color failed")
+    return out

@@ -55,4 +55,14 @@ double ref_flow_mse(const float* gt, const float* flow, int w, int h) {
   return f.CalculateMSE(a, b);
 }
 
+// Flow::MotionToColor (rw_flow.cpp:202-249) of the reference itself; out: h x w x 3 bytes.
+int ref_flow_color(const float* flow, int w, int h, float maxmotion, unsigned char* out) {
+  Flow f;
+  cv::Mat in(h, w, CV_32FC2, (void*)flow, (size_t)w * 8), img;
+  f.MotionToColor(in, img, maxmotion);
+  if (img.cols != w || img.rows != h) return -1;
+  for (int i = 0; i < h; ++i) memcpy(out + (size_t)i * w * 3, img.data + (size_t)i * img.step, (size_t)w * 3);
+  return 0;
+}
+
 }  // extern "C"

@@ -38,6 +38,10 @@ int main(int argc, char** argv) {
       mvs.at<cv::Vec2f>(i - pad_y, j - pad_x) = flow_res.at<cv::Vec2f>(i, j);
 
   Flow file;
+  // main_class.cpp:73-75: colour-code the field (main() hands the image to cv::imwrite)
+  cv::Mat flow_img;
+  file.MotionToColor(mvs, flow_img, -1);
+  if (flow_img.rows != h || flow_img.cols != w) return 5;
   file.WriteFlowFile(mvs, argv[5]);
   cv::Mat back;
   file.ReadFlowFile(back, argv[5]);

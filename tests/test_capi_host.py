@@ -155,3 +155,26 @@ def test_strip_and_subsample_like_main():
     px, py = sh["padding_x"], sh["padding_y"]
     want = flow[py:sh["padded_height"] - py:4, px:sh["padded_width"] - px:4] / 4.0
     assert np.array_equal(out, want)
+
+
+def test_motion_to_color_equals_the_reference():
+    """Flow::MotionToColor (rw_flow.cpp:202-300): bytes identical to what the reference's own function produced
+    (tests/golden/flow_color_ref.npz, made by make_color_golden.py from oracle/_ref) and, when oracle/_ref is present,
+    to the reference's function run now on fresh random fields."""
+    from oracle import binding as ob
+    d = np.load(os.path.join(GOLD, "flow_color_ref.npz"))
+    fl = bb.Flow()
+    n = len([k for k in d.files if k.startswith("flow_")])
+    assert n >= 4
+    for i in range(n):
+        got = fl.MotionToColor(d[f"flow_{i}"], float(d[f"maxmotion_{i}"][0]))
+        assert got.dtype == np.uint8 and got.shape == d[f"bgr_{i}"].shape
+        assert np.array_equal(got, d[f"bgr_{i}"]), (i, int((got != d[f"bgr_{i}"]).sum()))
+    assert np.array_equal(fl.MotionToColor(np.zeros((4, 5, 2), np.float32)), np.full((4, 5, 3), 255, np.uint8))  # zero flow is white
+    unknown = np.full((2, 2, 2), 1e10, np.float32)
+    assert not fl.MotionToColor(unknown).any()  # unknown flow is black
+    if ob.load_ref() is not None:
+        rng = np.random.default_rng(8)
+        for scale, mm in ((0.3, -1.0), (40.0, -1.0), (7.0, 2.5)):
+            f = (rng.standard_normal((33, 47, 2)) * scale).astype(np.float32)
+            assert np.array_equal(fl.MotionToColor(f, mm), ob.ref_flow_color(f, mm))
