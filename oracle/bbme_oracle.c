@@ -14,13 +14,17 @@
  *   cv::pyrDown(8-bit)                     -> orc_pyrdown: separable [1 4 6 4 1], BORDER_REFLECT_101,
  *                                             (sum + 128) >> 8
  *   cv::norm(a, b, NORM_L1) on CV_8UC1     -> exact integer sum of |a-b|
+ *   cv::resize(INTER_LINEAR, 8-bit)        -> orc_resize_linear (main()'s x4 up-sampling, main_class.cpp:32-33):
+ *                                             11-bit weights, int32 horizontal pass, two-shift vertical pass
  *
  * Parity pinning (what this oracle has been checked against):
  *   - oracle/_ref: the reference's own motion_framework.cpp / rw_flow.cpp compiled where they lie,
  *     against oracle/cvshim (a minimal own implementation of the cv:: subset they use); dense fields
- *     are compared bit-for-bit in tests/test_oracle_vs_reference.py and frozen in tests/golden/.
+ *     are compared bit-for-bit in tests/test_oracle.py and frozen in tests/golden/mf_reference.npz.
  *   - cv2 4.13.0 (this container's Python wheel) for pyrDown / copyMakeBorder / norm, frozen in
  *     tests/golden/pyrdown_*.npz by tests/golden/make_golden.py.
+ *   - cv2 4.13.0 for resize(INTER_LINEAR) at factors 2 / 4 / 8 (tests/golden/resize_cv2.npz by
+ *     tests/golden/make_resize_golden.py, plus a live cv2 comparison in tests/test_oracle.py).
  *   - the 8 Middlebury gt-flow .flo files for the .flo codec (byte-identical round trip).
  * The reference ships no golden motion fields of its own (it has no tests).
  *
