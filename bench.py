@@ -74,7 +74,7 @@ def make_pairs(n_distinct, rank):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed regions run."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -89,7 +89,7 @@ class ClockSampler:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=f, stderr=subprocess.DEVNULL)
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -263,7 +263,6 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     t_wall = time.perf_counter() - t_wall0
     est.sync()
-    clocks = sampler.stop()
     ms_total = ev0.elapsed_time(ev1)
     st = est.stats()  # of the LAST step (stats reset at each call)
     launches = st["kernel_launches"] * args.steps
@@ -359,6 +358,7 @@ def run_ours(args, rank, local_rank, world):
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop()  # sampled over both timed regions (device arm and host-buffer arm)
     e2e_value = world * P * e2e_steps / float(t.item()) if e2e_steps else None
     e2e_ok = None
     if rank == 0 and not args.no_check and e2e_steps:

@@ -308,7 +308,7 @@ int run_chunk(bbme_ctx* c, Slot& s, int n, const uint8_t* d_in1, const uint8_t* 
         launch_reg_full(ra, n, st);
         for (int r = 0; r < gr; ++r) launch_reg_round(ra, r, n, st);
         launch_reg_fix(ra, gr, n, st);
-        c->launches += 2 + gr;
+        c->launches += 3 + gr;  // classify + eval, gr grid-wide rounds, the per-pair tail loop
         short2* t = cur; cur = nxt; nxt = t;
       }
       if (g > 2) {
