@@ -178,3 +178,21 @@ def test_motion_to_color_equals_the_reference():
         for scale, mm in ((0.3, -1.0), (40.0, -1.0), (7.0, 2.5)):
             f = (rng.standard_normal((33, 47, 2)) * scale).astype(np.float32)
             assert np.array_equal(fl.MotionToColor(f, mm), ob.ref_flow_color(f, mm))
+
+
+def test_reference_main_compiles_against_dropin_headers(tmp_path):
+    """The reference's own main_class.cpp, unmodified, against include/ (MF, Flow incl. MotionToColor, the public ints):
+    syntax check only -- OpenCV itself is not installed, so cv::Mat comes from the test oracle's shim headers and
+    imread / resize / imwrite are declared by tests/cpp/opencv_io_stubs.hpp.  The reference's own class headers must not
+    sit next to main_class.cpp (quote includes look there first), hence the copy."""
+    ref = "/root/reference"
+    if not os.path.exists(os.path.join(ref, "main_class.cpp")):
+        pytest.skip("reference tree not present on this box")
+    import shutil
+    for f in ("main_class.cpp", "standard_headers.h", "opencv_headers.h"):
+        shutil.copy(os.path.join(ref, f), tmp_path / f)
+    res = subprocess.run(["g++", "-std=c++11", "-fsyntax-only", "-DBBME_USE_OPENCV", "-I" + os.path.join(ROOT, "include"),
+                          "-I" + os.path.join(ROOT, "oracle", "cvshim"), "-include",
+                          os.path.join(ROOT, "tests", "cpp", "opencv_io_stubs.hpp"), "main_class.cpp"],
+                         cwd=tmp_path, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-2000:]
