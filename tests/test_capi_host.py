@@ -196,3 +196,20 @@ def test_reference_main_compiles_against_dropin_headers(tmp_path):
                           os.path.join(ROOT, "tests", "cpp", "opencv_io_stubs.hpp"), "main_class.cpp"],
                          cwd=tmp_path, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr[-2000:]
+
+
+def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
+    """`bench.py --impl reference` (the reference's CPU path on this box's cores): exactly one line on stdout, JSON, with the
+    keys the driver reads.  Also covers the stdout hygiene (libraries must not get to print there)."""
+    res = subprocess.run([os.sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, res.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "1080p frame-pairs/sec" and d["unit"] == "pairs/s"
+    assert d["higher_is_better"] is True and d["steps"] == 1 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]
