@@ -204,3 +204,29 @@ def test_strip_subsample_follows_main(oracle):
             want[(i - py) // 4, (j - px) // 4] = flow[i, j] / np.float32(4)
     assert np.array_equal(oracle.strip_subsample(flow, px, py, 4), want)
     assert np.array_equal(bb.Flow().StripAndSubsample(flow, shape, 4), want)
+
+
+def test_oracle_fuzz_against_live_reference(oracle):
+    """Random geometries and contents: oracle port == the reference's own sources (oracle/_ref), bit for bit.  A short slice
+    of scripts/fuzz_oracle_vs_reference.py (which ran 16 918 cases without a mismatch in round 1)."""
+    if oracle.load_ref() is None:
+        pytest.skip("oracle/_ref not built")
+    import blockbasedmotionestimation_b200 as bb
+    rng = np.random.default_rng(2718)
+    done = 0
+    while done < 120:
+        L = int(rng.integers(1, 4))
+        bs = [int(2 ** rng.integers(1, 6)) for _ in range(L)]
+        ss = [b + int(rng.integers(0, 13)) for b in bs]
+        w, h = int(rng.integers(16, 200)), int(rng.integers(16, 160))
+        try:
+            bb.plan_shape(w, h, ss, bs)
+        except bb.BbmeError:
+            continue
+        kind = ["textured", "noise", "constant"][int(rng.integers(0, 3))]
+        f1, f2 = make_pair(h, w, int(rng.integers(0, 1 << 30)), shift=(int(rng.integers(-4, 5)), int(rng.integers(-4, 5))),
+                           max_patch_shift=4, kind=kind)
+        want = oracle.ref_estimate(f1, f2, ss, bs)[0]
+        got, _ = oracle.estimate(f1, f2, ss, bs, 2)
+        assert np.array_equal(got, want), (w, h, ss, bs, kind)
+        done += 1
