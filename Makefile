@@ -5,18 +5,21 @@ CSRC := $(PKG)/csrc
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function \
            --fmad=false -Iinclude
 LIB := $(PKG)/libbbme.so
-OBJS := $(CSRC)/kernels.o $(CSRC)/search_tma.o $(CSRC)/capi.o $(CSRC)/flo.o
+OBJS := $(CSRC)/kernels.o $(CSRC)/search_tma.o $(CSRC)/capi.o $(CSRC)/flo.o $(CSRC)/hostpool.o
 
 all: $(LIB) oracle
 
-$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/kernels.h include/bbme.h
+$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/kernels.h $(CSRC)/hostpool.h include/bbme.h
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@
 
 $(CSRC)/flo.o: $(CSRC)/flo.cpp include/bbme.h
 	g++ -O2 -ffp-contract=off -fPIC -std=c++17 -Wall -Iinclude -c $< -o $@
 
+$(CSRC)/hostpool.o: $(CSRC)/hostpool.cpp $(CSRC)/hostpool.h
+	g++ -O3 -fPIC -std=c++17 -Wall -c $< -o $@
+
 $(LIB): $(OBJS)
-	$(NVCC) -gencode arch=compute_100a,code=sm_100a -shared -o $@ $(OBJS) -cudart static
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -shared -o $@ $(OBJS) -cudart static -lpthread
 
 oracle:
 	$(MAKE) -C oracle

@@ -41,6 +41,11 @@ class BbmeOptions(C.Structure):
     ]
 
 
+class BbmeHostLink(C.Structure):
+    _fields_ = [("h2d_gbs", C.c_double), ("d2h_gbs", C.c_double), ("duplex_gbs_per_direction", C.c_double),
+                ("host_stream_write_gbs", C.c_double), ("host_threads", C.c_int)]
+
+
 # name -> (restype, argtypes); every symbol include/bbme.h declares
 _P = C.c_void_p
 _I = C.c_int
@@ -66,11 +71,13 @@ SIGNATURES = {
     "bbme_estimate_device": (_I, [_P, _I, _P, _P, _SZ, _SZ, _P, _SZ]),
     "bbme_estimate_device_compact": (_I, [_P, _I, _P, _P, _SZ, _SZ, _P, _SZ]),
     "bbme_estimate_device_both": (_I, [_P, _I, _P, _P, _SZ, _SZ, _P, _SZ, _P, _SZ]),
+    "bbme_expand_compact": (_I, [_P, _I, _I, _P]),
     "bbme_sync": (_I, [_P]),
     "bbme_get_stats": (_I, [_P, C.POINTER(BbmeStats)]),
     "bbme_set_streams": (_I, [_P, _I, C.POINTER(_P)]),
     "bbme_measure_int_peak": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "bbme_get_shape": (_I, [_P, C.POINTER(BbmeShape)]),
+    "bbme_measure_host_link": (_I, [_P, _SZ, C.POINTER(BbmeHostLink)]),
     "bbme_host_alloc": (_I, [C.POINTER(_P), _SZ]),
     "bbme_host_free": (None, [_P]),
     "bbme_debug_level_image": (_I, [_P, _I, _I, _I, _P]),

@@ -253,6 +253,12 @@ class Estimator:
         _check(self._lib, self._ctx, self._lib.bbme_measure_int_peak(self._ctx, C.byref(v), C.byref(f)), "bbme_measure_int_peak")
         return v.value, f.value
 
+    def measure_host_link(self, nbytes=256 << 20):
+        """Pinned H2D / D2H bandwidth and the worker threads' host write bandwidth (GB/s): the host-buffer path's ceilings."""
+        hl = _lib.BbmeHostLink()
+        _check(self._lib, self._ctx, self._lib.bbme_measure_host_link(self._ctx, int(nbytes), C.byref(hl)), "bbme_measure_host_link")
+        return {k: getattr(hl, k) for k, _ in _lib.BbmeHostLink._fields_}
+
     def sync(self):
         _check(self._lib, self._ctx, self._lib.bbme_sync(self._ctx), "bbme_sync")
 

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/bbme.h"
+#include "hostpool.h"
 #include "kernels.h"
 
 using namespace bbme;
@@ -35,7 +36,11 @@ struct Slot {
   uint32_t* ctr = nullptr;
   unsigned long long* counters = nullptr;  // [0] candidates, [1] absdiffs
   uint32_t* hist = nullptr;                // BBME_FIX_HIST=1: kHistSweeps x 64 words (RegArgs::hist)
-  float* out = nullptr;
+  float* out = nullptr;               // device output of the up-sampled path (stripped, sub-sampled field)
+  // host-buffer path: the compact int16 field is copied into a pinned staging buffer and expanded on the host
+  int16_t* stage[2] = {nullptr, nullptr};
+  Ticket* ticket[2] = {nullptr, nullptr};
+  int stage_turn = 0;
   TmaSearchPlan tma[kMaxLevels];
   TmaSearchPlan tma_seq[kMaxLevels];  // sequence mode: image 2 of pair i is plane i + 1 of the image-1 array
   std::vector<cudaEvent_t> ev;
@@ -121,6 +126,13 @@ int dev_alloc(bbme_ctx* c, T** p, size_t count, bool zero) {
 
 void release_plan(bbme_ctx* c) {
   for (Slot& s : c->slots) {
+    // after a failed stream the queued host functions may never run: leak the ticket rather than wait for ever
+    const bool drained = !s.stream || cudaStreamSynchronize(s.stream) == cudaSuccess;
+    for (int j = 0; j < 2; ++j) {
+      if (s.ticket[j] && drained) { s.ticket[j]->wait(); delete s.ticket[j]; }
+      s.ticket[j] = nullptr;
+      if (s.stage[j]) { cudaFreeHost(s.stage[j]); s.stage[j] = nullptr; }
+    }
     for (cudaEvent_t e : s.ev) cudaEventDestroy(e);
     for (auto& g : s.graphs) cudaGraphExecDestroy(g.exec);
     s.graphs.clear();
@@ -430,6 +442,64 @@ int collect_after_sync(bbme_ctx* c) {
 
 int sync_all(bbme_ctx* c) {
   for (Slot& s : c->slots) CUDA_TRY(c, cudaStreamSynchronize(s.stream));
+  // host functions are stream-ordered: every expansion has been queued by now; wait for the worker threads
+  for (Slot& s : c->slots)
+    for (int j = 0; j < 2; ++j)
+      if (s.ticket[j]) s.ticket[j]->wait();
+  return BBME_OK;
+}
+
+// Dense result of a chunk into the callers' host buffers (motion_framework.cpp:218: padded CV_32FC2, every 2x2 block one
+// vector): D2H of the 2x2-granular int16 field the schedule ends with (1/8 of the dense bytes) into a pinned staging
+// buffer, then a stream-ordered host function hands the expansion (int16 -> float, 2x2 replication) to the worker threads.
+struct ExpandJob {
+  const int16_t* stage;
+  std::vector<float*> dst;
+  int gw2, gh2;
+  size_t pw, plane;  // plane: int16 per pair in the staging buffer
+  Ticket* ticket;
+};
+
+void CUDART_CB expand_cb(void* p) {
+  ExpandJob* j = static_cast<ExpandJob*>(p);
+  HostPool& pool = HostPool::instance();
+  for (size_t i = 0; i < j->dst.size(); ++i)
+    pool.expand_async(j->stage + i * j->plane, j->gw2, j->gh2, j->dst[i], j->pw, j->ticket);
+  j->ticket->done(1);  // the job's own reference
+  delete j;
+}
+
+int enqueue_dense_result(bbme_ctx* c, Slot& s, int m, float* const* flow) {
+  const size_t plane = c->cap[0] * 2;  // int16 per pair
+  const int turn = s.stage_turn;
+  if (!s.stage[turn]) {
+    void* q = nullptr;
+    const size_t bytes = (size_t)c->opt.chunk_pairs * plane * sizeof(int16_t);
+    if (cudaHostAlloc(&q, bytes, cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(c, BBME_E_NOMEM, "cudaHostAlloc(%zu bytes) for the result staging buffer failed", bytes);
+    }
+    s.stage[turn] = static_cast<int16_t*>(q);
+    s.ticket[turn] = new Ticket();
+  }
+  s.ticket[turn]->wait();  // the chunk that used this staging buffer two turns ago has been expanded
+  CUDA_TRY(c, cudaMemcpyAsync(s.stage[turn], s.mv_final[0], (size_t)m * plane * sizeof(int16_t), cudaMemcpyDeviceToHost, s.stream));
+  ExpandJob* j = new ExpandJob();
+  j->stage = s.stage[turn];
+  j->dst.assign(flow, flow + m);
+  j->gw2 = c->shape.padded_width / 2;
+  j->gh2 = c->shape.padded_height / 2;
+  j->pw = (size_t)c->shape.padded_width;
+  j->plane = plane;
+  j->ticket = s.ticket[turn];
+  j->ticket->add(1);
+  cudaError_t e = cudaLaunchHostFunc(s.stream, expand_cb, j);
+  if (e != cudaSuccess) {
+    j->ticket->done(1);
+    delete j;
+    return fail(c, BBME_E_CUDA, "cudaLaunchHostFunc failed: %s", cudaGetErrorString(e));
+  }
+  s.stage_turn ^= 1;
   return BBME_OK;
 }
 
@@ -570,7 +640,7 @@ int bbme_plan(bbme_ctx* c, int width, int height, int num_levels, const int* sea
     if ((rc = dev_alloc(c, &s.list0, n * c->cap[0], false)) || (rc = dev_alloc(c, &s.list1, n * c->cap[0], false)) ||
         (rc = dev_alloc(c, &s.nv, n * c->cap[0], false)) || (rc = dev_alloc(c, &s.stamp, n * c->cap[0], true)) ||
         (rc = dev_alloc(c, &s.ctr, n * kCtrWords, true)) || (rc = dev_alloc(c, &s.counters, (size_t)2, true)) ||
-        (rc = dev_alloc(c, &s.out, n * c->out_plane, false)))
+        (rc = dev_alloc(c, &s.out, n * (c->out_plane / 4 + 64), false)))
       return rc;
     if (getenv("BBME_FIX_HIST") && (rc = dev_alloc(c, &s.hist, (size_t)kHistSweeps * 64, true))) return rc;
     for (int l = 0; l < L; ++l) {
@@ -641,6 +711,62 @@ int bbme_measure_int_peak(bbme_ctx* c, double* absdiff_per_s, double* sm_mhz) {
   return BBME_OK;
 }
 
+int bbme_measure_host_link(bbme_ctx* c, size_t bytes, bbme_host_link* out) {
+  if (!c || !out || bytes < (1u << 20)) return BBME_E_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  memset(out, 0, sizeof(*out));
+  void *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr;
+  cudaStream_t s0 = nullptr, s1 = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int rc = BBME_OK;
+  auto time_ms = [&](int mode) -> float {  // 0 = H2D, 1 = D2H, 2 = both directions at once
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+      cudaDeviceSynchronize();
+      cudaEventRecord(e0, s0);
+      cudaStreamWaitEvent(s1, e0, 0);
+      if (mode != 1) cudaMemcpyAsync(d_in, h_in, bytes, cudaMemcpyHostToDevice, s0);
+      if (mode != 0) cudaMemcpyAsync(h_out, d_out, bytes, cudaMemcpyDeviceToHost, s1);
+      cudaEventRecord(e1, s1);
+      cudaStreamWaitEvent(s0, e1, 0);
+      cudaEventRecord(e1, s0);
+      cudaStreamSynchronize(s0);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (ms > 0.f && ms < best) best = ms;
+    }
+    return best;
+  };
+  if (cudaHostAlloc(&h_in, bytes, cudaHostAllocDefault) != cudaSuccess || cudaHostAlloc(&h_out, bytes, cudaHostAllocDefault) != cudaSuccess ||
+      cudaMalloc(&d_in, bytes) != cudaSuccess || cudaMalloc(&d_out, bytes) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&s0, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&e0) != cudaSuccess ||
+      cudaEventCreate(&e1) != cudaSuccess) {
+    cudaGetLastError();
+    rc = fail(c, BBME_E_NOMEM, "bbme_measure_host_link: allocation of %zu-byte test buffers failed", bytes);
+  } else {
+    memset(h_in, 1, bytes);
+    memset(h_out, 1, bytes);
+    const double gb = (double)bytes / 1e9;
+    out->h2d_gbs = gb / (time_ms(0) * 1e-3);
+    out->d2h_gbs = gb / (time_ms(1) * 1e-3);
+    out->duplex_gbs_per_direction = gb / (time_ms(2) * 1e-3);
+    HostPool& pool = HostPool::instance();
+    out->host_threads = pool.threads();
+    out->host_stream_write_gbs = pool.measure_stream_write(h_out, bytes, 3);
+    if (cudaGetLastError() != cudaSuccess) rc = fail(c, BBME_E_CUDA, "bbme_measure_host_link: CUDA error during the copies");
+  }
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (s0) cudaStreamDestroy(s0);
+  if (s1) cudaStreamDestroy(s1);
+  if (d_in) cudaFree(d_in);
+  if (d_out) cudaFree(d_out);
+  if (h_in) cudaFreeHost(h_in);
+  if (h_out) cudaFreeHost(h_out);
+  return rc;
+}
+
 int bbme_get_stats(bbme_ctx* c, bbme_stats* out) {
   if (!c || !out) return BBME_E_ARG;
   *out = c->stats;
@@ -675,10 +801,15 @@ static int estimate_batch_async_impl(bbme_ctx* c, int n, int factor, const uint8
       CUDA_TRY(c, cudaMemcpy2DAsync(s.in2 + (size_t)i * in_plane, in_pitch, im2[start + i], pitch, w, h,
                                     cudaMemcpyHostToDevice, s.stream));
     }
-    int rc = run_chunk_graphed(c, s, m, s.in1, s.in2, in_pitch, in_plane, s.out, out_plane, nullptr, 0, factor);
-    if (rc) return rc;
-    for (int i = 0; i < m; ++i)
-      CUDA_TRY(c, cudaMemcpyAsync(flow[start + i], s.out + (size_t)i * out_plane, flow_bytes, cudaMemcpyDeviceToHost, s.stream));
+    if (factor > 1) {
+      int rc = run_chunk_graphed(c, s, m, s.in1, s.in2, in_pitch, in_plane, s.out, out_plane, nullptr, 0, factor);
+      if (rc) return rc;
+      for (int i = 0; i < m; ++i)
+        CUDA_TRY(c, cudaMemcpyAsync(flow[start + i], s.out + (size_t)i * out_plane, flow_bytes, cudaMemcpyDeviceToHost, s.stream));
+    } else {
+      int rc = run_chunk_graphed(c, s, m, s.in1, s.in2, in_pitch, in_plane, nullptr, 0, nullptr, 0, 1);
+      if (rc || (rc = enqueue_dense_result(c, s, m, flow + start))) return rc;
+    }
   }
   c->next_slot = ci % (int)c->slots.size();
   return BBME_OK;
@@ -715,7 +846,6 @@ int bbme_estimate_sequence_async(bbme_ctx* c, int n_frames, const uint8_t* const
   CUDA_TRY(c, cudaSetDevice(c->device));
   begin_call(c);
   const int chunk = c->opt.chunk_pairs, n = n_frames - 1;
-  const size_t flow_bytes = c->out_plane * sizeof(float);
   int ci = c->next_slot;
   for (int start = 0; start < n; start += chunk, ++ci) {
     Slot& s = c->slots[ci % c->slots.size()];
@@ -723,10 +853,8 @@ int bbme_estimate_sequence_async(bbme_ctx* c, int n_frames, const uint8_t* const
     for (int i = 0; i <= m; ++i)
       CUDA_TRY(c, cudaMemcpy2DAsync(s.in1 + (size_t)i * c->in_plane, c->in_pitch, frames[start + i], pitch, c->shape.width,
                                     c->shape.height, cudaMemcpyHostToDevice, s.stream));
-    int rc = run_chunk_graphed(c, s, m, s.in1, nullptr, c->in_pitch, c->in_plane, s.out, c->out_plane, nullptr, 0, 1, true);
-    if (rc) return rc;
-    for (int i = 0; i < m; ++i)
-      CUDA_TRY(c, cudaMemcpyAsync(flow[start + i], s.out + (size_t)i * c->out_plane, flow_bytes, cudaMemcpyDeviceToHost, s.stream));
+    int rc = run_chunk_graphed(c, s, m, s.in1, nullptr, c->in_pitch, c->in_plane, nullptr, 0, nullptr, 0, 1, true);
+    if (rc || (rc = enqueue_dense_result(c, s, m, flow + start))) return rc;
   }
   c->next_slot = ci % (int)c->slots.size();
   return BBME_OK;
@@ -833,6 +961,14 @@ int bbme_estimate_device_both(bbme_ctx* c, int n, const uint8_t* d1, const uint8
                               float* d_flow, size_t flow_plane, int16_t* d_mv, size_t mv_plane) {
   if (!d_flow && !d_mv) return c ? fail(c, BBME_E_ARG, "bbme_estimate_device_both: no output buffer") : BBME_E_ARG;
   return estimate_device_impl(c, n, d1, d2, pitch, plane, d_flow, flow_plane, d_mv, mv_plane);
+}
+
+int bbme_expand_compact(const int16_t* mv2, int width2, int height2, float* dense) {
+  if (!mv2 || !dense || width2 <= 0 || height2 <= 0) return BBME_E_ARG;
+  Ticket t;
+  HostPool::instance().expand_async(mv2, width2, height2, dense, (size_t)width2 * 2, &t);
+  t.wait();
+  return BBME_OK;
 }
 
 int bbme_host_alloc(void** p, size_t bytes) {

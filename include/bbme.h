@@ -27,7 +27,7 @@ extern "C" {
 #endif
 
 #define BBME_MAX_LEVELS 16
-#define BBME_VERSION 101
+#define BBME_VERSION 200
 
 typedef enum {
   BBME_OK = 0,
@@ -157,6 +157,11 @@ int bbme_estimate_upsampled_device(bbme_ctx* ctx, int n, int factor, const uint8
 int bbme_estimate_device_compact(bbme_ctx* ctx, int n, const uint8_t* d_im1, const uint8_t* d_im2,
                                  size_t pitch_bytes, size_t plane_stride, int16_t* d_mv, size_t mv_plane_stride);
 
+/* Host-side expansion of a compact field into the dense CV_32FC2 layout (motion_framework.cpp:205-206,218): width2 x height2
+ * int16 (u, v) entries -> (2 * height2) x (2 * width2) x 2 floats, every 2x2 pixel block one vector.  Runs on the library's
+ * worker threads (the same code the host-buffer entry points use after their D2H copy); needs no GPU. */
+int bbme_expand_compact(const int16_t* mv2, int width2, int height2, float* dense);
+
 /* Both outputs of one run: the dense field (may be NULL) and the compact field (may be NULL), at least one given. */
 int bbme_estimate_device_both(bbme_ctx* ctx, int n, const uint8_t* d_im1, const uint8_t* d_im2, size_t pitch_bytes,
                               size_t plane_stride, float* d_flow, size_t flow_plane_stride, int16_t* d_mv,
@@ -173,6 +178,17 @@ int bbme_set_streams(bbme_ctx* ctx, int n, void* const* streams);
  * every SM, ~1 ms): the integer roofline denominator, in |a-b| per second.  Also returns the SM clock it ran at. */
 int bbme_measure_int_peak(bbme_ctx* ctx, double* absdiff_per_s, double* sm_mhz);
 int bbme_get_shape(const bbme_ctx* ctx, bbme_shape* out);
+
+/* The ceilings of the host-buffer entry points, measured on this box: pinned H2D and D2H copies of `bytes` bytes (alone and
+ * both directions at once) and the worker threads' non-temporal write bandwidth into host memory.  bbme_estimate_batch moves,
+ * per pair, 2*W*H bytes H2D and padded_w*padded_h/2 bytes D2H (the 2x2-granular int16 field) and writes the dense
+ * 8*padded_w*padded_h-byte CV_32FC2 field (motion_framework.cpp:218) into the caller's buffer with the worker threads. */
+typedef struct {
+  double h2d_gbs, d2h_gbs, duplex_gbs_per_direction;
+  double host_stream_write_gbs;
+  int host_threads;
+} bbme_host_link;
+int bbme_measure_host_link(bbme_ctx* ctx, size_t bytes, bbme_host_link* out);
 
 /* Pinned host memory for asynchronous copies. */
 int bbme_host_alloc(void** p, size_t bytes);

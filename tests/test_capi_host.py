@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
     exported = set(re.findall(r" T (bbme_[a-z0-9_]+)", out))
     assert set(declared) <= exported, sorted(set(declared) - exported)
     assert set(declared) == set(_lib.SIGNATURES), sorted(set(declared) ^ set(_lib.SIGNATURES))
-    assert lib.bbme_version() == 101
+    assert lib.bbme_version() == 200
 
 
 def test_library_contains_sm100a_code_only():
@@ -213,3 +213,18 @@ def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+
+
+def test_expand_compact_matches_numpy():
+    """The host-side expansion behind the host-buffer entry points (compact int16 D2H + worker threads): every 2x2 pixel
+    block of the dense CV_32FC2 field carries its entry's vector (motion_framework.cpp:205-206)."""
+    lib = _lib.load()
+    rng = np.random.default_rng(7)
+    for gh2, gw2, align in [(3, 5, 0), (64, 96, 0), (77, 130, 0), (544, 960, 0), (33, 36, 4)]:
+        mv = rng.integers(-2000, 2000, (gh2, gw2, 2)).astype(np.int16)
+        buf = np.full(2 * gh2 * 2 * gw2 * 2 + 16, np.nan, np.float32)
+        out = buf[align:align + 2 * gh2 * 2 * gw2 * 2].reshape(2 * gh2, 2 * gw2, 2)  # align = 4 floats: not 32-byte aligned
+        assert lib.bbme_expand_compact(mv.ctypes.data, gw2, gh2, out.ctypes.data) == 0
+        want = np.repeat(np.repeat(mv, 2, axis=0), 2, axis=1).astype(np.float32)
+        assert np.array_equal(out, want)
+        assert np.isnan(buf[:align]).all() and np.isnan(buf[align + out.size:]).all()
