@@ -5,7 +5,7 @@ CSRC := $(PKG)/csrc
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function \
            --fmad=false -Iinclude
 LIB := $(PKG)/libbbme.so
-OBJS := $(CSRC)/kernels.o $(CSRC)/search_tma.o $(CSRC)/capi.o $(CSRC)/flo.o $(CSRC)/hostpool.o
+OBJS := $(CSRC)/kernels.o $(CSRC)/search_tma.o $(CSRC)/capi.o $(CSRC)/flo.o $(CSRC)/hostpool.o $(CSRC)/multi.o
 
 all: $(LIB) oracle
 
@@ -17,6 +17,9 @@ $(CSRC)/flo.o: $(CSRC)/flo.cpp include/bbme.h
 
 $(CSRC)/hostpool.o: $(CSRC)/hostpool.cpp $(CSRC)/hostpool.h
 	g++ -O3 -fPIC -std=c++17 -Wall -c $< -o $@
+
+$(CSRC)/multi.o: $(CSRC)/multi.cpp include/bbme.h
+	g++ -O2 -fPIC -std=c++17 -Wall -Iinclude -c $< -o $@
 
 $(LIB): $(OBJS)
 	$(NVCC) -gencode arch=compute_100a,code=sm_100a -shared -o $@ $(OBJS) -cudart static -lpthread

@@ -78,6 +78,15 @@ SIGNATURES = {
     "bbme_measure_int_peak": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "bbme_get_shape": (_I, [_P, C.POINTER(BbmeShape)]),
     "bbme_measure_host_link": (_I, [_P, _SZ, C.POINTER(BbmeHostLink)]),
+    "bbme_mf_open": (_I, [C.POINTER(_P), _I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), _I, C.POINTER(BbmeShape)]),
+    "bbme_mf_close": (None, [_P]),
+    "bbme_mf_cache_clear": (None, []),
+    "bbme_pool_create": (_I, [C.POINTER(_P), _I, C.POINTER(_I)]),
+    "bbme_pool_destroy": (None, [_P]),
+    "bbme_pool_device_count": (_I, [_P]),
+    "bbme_pool_last_error": (C.c_char_p, [_P]),
+    "bbme_pool_plan": (_I, [_P, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(BbmeOptions), C.POINTER(BbmeShape)]),
+    "bbme_pool_estimate_batch": (_I, [_P, _I, C.POINTER(_P), C.POINTER(_P), _SZ, C.POINTER(_P)]),
     "bbme_host_alloc": (_I, [C.POINTER(_P), _SZ]),
     "bbme_host_free": (None, [_P]),
     "bbme_debug_level_image": (_I, [_P, _I, _I, _I, _P]),

@@ -337,6 +337,69 @@ class Estimator:
         return out
 
 
+class Pool:
+    """All GPUs of the box behind one call (bbme_pool_*): the batch is cut into contiguous shards, one host thread per GPU
+    runs its shard, the fields land in host arrays.  Frame pairs are independent, so nothing moves between GPUs."""
+
+    def __init__(self, width, height, search_size, block_size, num_levels=None, sweeps=2, devices=None, chunk_pairs=8, slots=2):
+        self._lib = _lib.load()
+        self._pool = C.c_void_p()
+        n = 0 if devices is None else len(devices)
+        rc = self._lib.bbme_pool_create(C.byref(self._pool), n, None if devices is None else _int_array(devices))
+        if rc != 0:
+            msg = self._lib.bbme_last_error(None)
+            raise BbmeError(rc, "bbme_pool_create: " + (msg.decode() if msg else ""))
+        L = len(block_size) if num_levels is None else int(num_levels)
+        opt = BbmeOptions()
+        self._lib.bbme_default_options(C.byref(opt))
+        opt.sweeps, opt.chunk_pairs, opt.slots = int(sweeps), int(chunk_pairs), int(slots)
+        sh = BbmeShape()
+        rc = self._lib.bbme_pool_plan(self._pool, int(width), int(height), L, _int_array(search_size[:L]),
+                                      _int_array(block_size[:L]), C.byref(opt), C.byref(sh))
+        if rc != 0:
+            msg = self._lib.bbme_pool_last_error(self._pool).decode()
+            self.close()
+            raise BbmeError(rc, "bbme_pool_plan: " + msg)
+        self.shape = _shape_dict(sh)
+        self.device_count = self._lib.bbme_pool_device_count(self._pool)
+
+    def close(self):
+        if getattr(self, "_pool", None) is not None and self._pool:
+            self._lib.bbme_pool_destroy(self._pool)
+            self._pool = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def estimate_batch(self, im1_list, im2_list):
+        n = len(im1_list)
+        h, w = self.shape["height"], self.shape["width"]
+        PA = C.c_void_p * n
+        p1, p2, po = PA(), PA(), PA()
+        outs = [np.empty((self.shape["padded_height"], self.shape["padded_width"], 2), np.float32) for _ in range(n)]
+        keep = []
+        for i in range(n):
+            a = np.ascontiguousarray(im1_list[i], np.uint8)
+            b = np.ascontiguousarray(im2_list[i], np.uint8)
+            if a.shape != (h, w) or b.shape != (h, w):
+                raise BbmeError(-1, f"frames must be uint8 {h}x{w}")
+            keep += [a, b]
+            p1[i], p2[i], po[i] = a.ctypes.data, b.ctypes.data, outs[i].ctypes.data
+        rc = self._lib.bbme_pool_estimate_batch(self._pool, n, p1, p2, w, po)
+        if rc != 0:
+            raise BbmeError(rc, "bbme_pool_estimate_batch: " + self._lib.bbme_pool_last_error(self._pool).decode())
+        return outs
+
+
 class MF:
     """Mirror of `class MF` (motion_framework.h:9-54).
 

@@ -83,6 +83,7 @@ struct bbme_ctx {
   bool stats_armed = false;
   int use_graphs = 1;   // small chunks replay a captured CUDA graph of their ~70-230 launches (BBME_GRAPHS=0 disables)
   int next_slot = 0;    // round-robin position over the slots across asynchronous calls
+  int reg_legacy = 0;    // BBME_REG_LEGACY=1: the per-sweep kernels of round 1 instead of the fused level kernel (A/B runs)
   int grid_rounds = -1;  // fix-up rounds run grid-wide before the per-pair tail loop; -1 = by chunk size (BBME_GRID_ROUNDS)
 };
 
@@ -274,7 +275,7 @@ int run_chunk(bbme_ctx* c, Slot& s, int n, const uint8_t* d_in1, const uint8_t* 
     int g = bs0, gw = lw / g, gh = lh / g;
     MvView field{cur, gw, gh, c->cap[l]};
     if (l == L - 1) {
-      cudaMemsetAsync(cur, 0, (size_t)n * c->cap[l] * sizeof(short2), st);  // level_flow starts at zero (:70,92)
+      CUDA_TRY(c, cudaMemsetAsync(cur, 0, (size_t)n * c->cap[l] * sizeof(short2), st));  // level_flow starts at zero (:70,92)
     } else {
       launch_copy_mvs(s.mv_final[l + 1], sh.level_width[l + 1] / 2, c->cap[l + 1], sh.block_size[l + 1], field, g, n, st);
       ++c->launches;
@@ -283,18 +284,42 @@ int run_chunk(bbme_ctx* c, Slot& s, int n, const uint8_t* d_in1, const uint8_t* 
     const TmaSearchPlan& tplan = seq ? s.tma_seq[l] : s.tma[l];
     const bool use_tma = tplan.supported && c->opt.search_kernel != 1;
     unsigned long long* ctrs = c->opt.collect_stats ? s.counters : nullptr;
-    if (use_tma) launch_search_tma(tplan, i1, i2, field, n, ctrs, c->sm_count, st);
-    else launch_search_generic(i1, i2, field, g, R, n, ctrs, st);
+    if (use_tma) {
+      if (launch_search_tma(tplan, i1, i2, field, n, ctrs, c->sm_count, st) != 0)
+        return fail(c, BBME_E_CUDA, "level %d: no TMA search kernel for block %d, R %d (plan and launch disagree)", l, g, R);
+    } else {
+      launch_search_generic(i1, i2, field, g, R, n, ctrs, st);
+    }
     ++c->launches;
     ++c->search_launches;
     mark(c, s, TAG_SEARCH);
     if (c->opt.keep_search_mv && s.mv_search[l]) {
-      cudaMemcpy2DAsync(s.mv_search[l], (size_t)gw * gh * sizeof(short2), cur, c->cap[l] * sizeof(short2),
-                        (size_t)gw * gh * sizeof(short2), n, cudaMemcpyDeviceToDevice, st);
+      CUDA_TRY(c, cudaMemcpy2DAsync(s.mv_search[l], (size_t)gw * gh * sizeof(short2), cur, c->cap[l] * sizeof(short2),
+                                    (size_t)gw * gh * sizeof(short2), n, cudaMemcpyDeviceToDevice, st));
     }
     // regularisation schedule (motion_framework.cpp:133-154): per block size `sweeps` sweeps with
     // lambda_multiplier 1..sweeps, then split; lambda starts at bs/2 (integer division, :73,95) and doubles.
     float lambda = (float)(bs0 / 2);
+    if (!c->reg_legacy) {
+      // one launch per level: a cluster of CTAs per pair walks through every sweep, fix-up round and split
+      RegArgs ra;
+      ra.i1 = i1; ra.i2 = i2;
+      ra.bs = g; ra.gw = gw; ra.gh = gh;
+      ra.lm = 0.f;
+      ra.O = cur; ra.Y = nxt;
+      ra.mv_plane = c->cap[l];
+      ra.list0 = s.list0; ra.list1 = s.list1; ra.nv = s.nv; ra.stamp = s.stamp;
+      ra.wl_plane = c->cap[0];
+      ra.ctr = s.ctr;
+      ra.hist = nullptr;
+      if (launch_reg_level(ra, c->opt.sweeps, lambda, 1, 0, n, c->sm_count, st) != 0)
+        return fail(c, BBME_E_CUDA, "regularisation kernel launch failed at level %d: %s", l, cudaGetErrorString(cudaGetLastError()));
+      ++c->launches;
+      int swaps = 0;
+      for (int gg = g; gg > 1; gg >>= 1) swaps += c->opt.sweeps + (gg > 2 ? 1 : 0);
+      if (swaps & 1) cur = nxt;
+      g = 1;
+    }
     while (g > 1) {
       for (int sw = 1; sw <= c->opt.sweeps; ++sw) {
         RegArgs ra;
@@ -578,6 +603,7 @@ int bbme_create(bbme_ctx** out, int device) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   if (const char* g = getenv("BBME_GRAPHS")) c->use_graphs = atoi(g) != 0;
+  if (const char* rl = getenv("BBME_REG_LEGACY")) c->reg_legacy = atoi(rl) != 0;
   if (const char* gr = getenv("BBME_GRID_ROUNDS")) {
     const int v = atoi(gr);
     if (v >= 0 && v <= 64) c->grid_rounds = v;
@@ -1112,8 +1138,11 @@ int bbme_stage_search(bbme_ctx* c, const uint8_t* im1, const uint8_t* im2, int w
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
   cudaEventRecord(e0, 0);
-  if (plan.supported) launch_search_tma(plan, i1, i2, f, 1, ctr, c->sm_count, 0);
-  else launch_search_generic(i1, i2, f, bs, R, 1, ctr, 0);
+  if (plan.supported) {
+    if (launch_search_tma(plan, i1, i2, f, 1, ctr, c->sm_count, 0) != 0) return fail(c, BBME_E_CUDA, "stage_search: TMA kernel launch failed");
+  } else {
+    launch_search_generic(i1, i2, f, bs, R, 1, ctr, 0);
+  }
   cudaEventRecord(e1, 0);
   cudaError_t e = cudaDeviceSynchronize();
   float ms = 0.f;
@@ -1163,10 +1192,16 @@ int bbme_stage_regularize(bbme_ctx* c, const uint8_t* im1, const uint8_t* im2, i
   ra.lm = lambda * (float)mult;
   ra.O = O; ra.Y = Y; ra.mv_plane = nb;
   ra.list0 = l0; ra.list1 = l1; ra.nv = nv; ra.stamp = stamp; ra.wl_plane = nb; ra.ctr = ctr;
-  const int gr = c->grid_rounds >= 0 ? c->grid_rounds : 3;
-  launch_reg_full(ra, 1, 0);
-  for (int r = 0; r < gr; ++r) launch_reg_round(ra, r, 1, 0);
-  launch_reg_fix(ra, gr, 1, 0);
+  if (!c->reg_legacy) {
+    ra.lm = 0.f;
+    if (launch_reg_level(ra, 1, lambda, mult, 1, 1, c->sm_count, 0) != 0)
+      return fail(c, BBME_E_CUDA, "stage_regularize launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  } else {
+    const int gr = c->grid_rounds >= 0 ? c->grid_rounds : 3;
+    launch_reg_full(ra, 1, 0);
+    for (int r = 0; r < gr; ++r) launch_reg_round(ra, r, 1, 0);
+    launch_reg_fix(ra, gr, 1, 0);
+  }
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return fail(c, BBME_E_CUDA, "stage_regularize kernel failed: %s", cudaGetErrorString(e));
   CUDA_TRY(c, cudaMemcpy(mv, Y, nb * sizeof(short2), cudaMemcpyDeviceToHost));

@@ -5,8 +5,10 @@
 // fields, and the in-place raster sweep is reproduced by a Jacobi pass followed by fixed-point rounds.
 #include "kernels.h"
 
+#include <cooperative_groups.h>
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace bbme {
 
@@ -498,7 +500,7 @@ void launch_export_subsample(const short2* mv2, int gw2, size_t mv_plane, int pa
 // Small blocks (2x2, 4x4: 95 % of all block evaluations) are evaluated by one thread; the only branch is
 // warp-uniform (every lane's nine candidates identical -> nothing can change).
 template <int BS>  // 2 or 4
-__device__ __forceinline__ short2 reg_eval_small(const RegArgs& a, int pair, const short2* __restrict__ O,
+__device__ __forceinline__ short2 reg_eval_small(const RegArgs& a, int pair, const short2* O,
                                                  const short2* P, int bx, int by, bool live) {
   const int gw = a.gw, gh = a.gh;
   const int idx = by * gw + bx;
@@ -566,29 +568,83 @@ __device__ __forceinline__ short2 reg_eval_small(const RegArgs& a, int pair, con
 #pragma unroll
     for (int r = 0; r < (BS == 2 ? 1 : 4); ++r) A[r] = *reinterpret_cast<const uint32_t*>(blk + (size_t)r * pitch);
   }
+  // A listed block has 2-4 DISTINCT vectors among its nine candidates (2.3 on average: it sits on the border between
+  // two or three motion layers), and the SAD depends on the vector only: the window of slot i is loaded only if no
+  // earlier slot holds the same vector ("need"), the others copy the SAD.  All needed windows are still addressed first
+  // and loaded together (predicated loads), so an evaluation stays one memory round trip.
+  uint32_t pk[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) pk[i] = pack_mv(c[i]);
+  bool inb[9], need[9];
+  const uint8_t* bp[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const int px = x + cx[i], py = y + cy[i];
+    inb[i] = (unsigned)px <= (unsigned)(w - BS) && (unsigned)py <= (unsigned)(h - BS);  // :578
+    bool dup = false;
+#pragma unroll
+    for (int j = 0; j < i; ++j) dup = dup || pk[j] == pk[i];
+    need[i] = inb[i] && !dup;
+    bp[i] = ref + (size_t)(need[i] ? py : y) * pitch + (need[i] ? px : x);
+  }
+  uint32_t sadv[9];
+  if (BS == 2) {
+    // a 2x2 window row is two bytes at any alignment: the aligned word that holds the first byte, plus the next word
+    // only when the row starts at byte 3
+    uint32_t w0[9][2], w1[9][2], sh[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const uintptr_t ab = reinterpret_cast<uintptr_t>(bp[i]);
+      sh[i] = (uint32_t)(ab & 3);
+      const uint32_t* q = reinterpret_cast<const uint32_t*>(ab & ~(uintptr_t)3);
+      const bool two = need[i] && sh[i] == 3u;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const uint32_t* qr = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(q) + (size_t)r * pitch);
+        w0[i][r] = need[i] ? qr[0] : 0u;
+        w1[i][r] = two ? qr[1] : 0u;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const uint32_t r0 = __funnelshift_r(w0[i][0], w1[i][0], sh[i] * 8u) & 0xffffu;
+      const uint32_t r1 = __funnelshift_r(w0[i][1], w1[i][1], sh[i] * 8u) & 0xffffu;
+      sadv[i] = sad4(A[0], r0 | (r1 << 16), 0u);
+    }
+  } else {
+    uint32_t w0[9][4], w1[9][4], sh[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const uintptr_t ab = reinterpret_cast<uintptr_t>(bp[i]);
+      sh[i] = (uint32_t)(ab & 3);
+      const uint32_t* q = reinterpret_cast<const uint32_t*>(ab & ~(uintptr_t)3);
+      const bool two = need[i] && sh[i] != 0u;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const uint32_t* qr = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(q) + (size_t)r * pitch);
+        w0[i][r] = need[i] ? qr[0] : 0u;
+        w1[i][r] = two ? qr[1] : 0u;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      uint32_t sad = 0;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) sad = sad4(A[r % (BS == 2 ? 1 : 4)], __funnelshift_r(w0[i][r], w1[i][r], sh[i] * 8u), sad);
+      sadv[i] = sad;
+    }
+  }
+  // duplicates copy the SAD of an earlier slot with the same vector (every earlier copy already holds it)
+#pragma unroll
+  for (int i = 1; i < 9; ++i) {
+#pragma unroll
+    for (int j = 0; j < i; ++j) sadv[i] = (pk[j] == pk[i]) ? sadv[j] : sadv[i];
+  }
   float best = 0.f;
   int best_i = 0;
 #pragma unroll
   for (int i = 0; i < 9; ++i) {
-    const int px = x + cx[i], py = y + cy[i];
-    const bool inb = (unsigned)px <= (unsigned)(w - BS) && (unsigned)py <= (unsigned)(h - BS);  // :578
-    const uint8_t* b = ref + (size_t)(inb ? py : y) * pitch + (inb ? px : x);  // out-of-image candidates read the block's own position
-    uint32_t sad;
-    if (BS == 2) {
-      const uint32_t bv = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[pitch] << 16) | ((uint32_t)b[pitch + 1] << 24);
-      sad = sad4(A[0], bv, 0u);
-    } else {
-      sad = 0;
-      const uintptr_t ab = reinterpret_cast<uintptr_t>(b);
-      const uint32_t sh = (uint32_t)(ab & 3) * 8u;
-      const uint32_t* bw = reinterpret_cast<const uint32_t*>(ab & ~(uintptr_t)3);
-#pragma unroll
-      for (int r = 0; r < (BS == 2 ? 1 : 4); ++r) {
-        const uint32_t* rw = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(bw) + (size_t)r * pitch);
-        sad = sad4(A[r], __funnelshift_r(rw[0], rw[1], sh), sad);
-      }
-    }
-    const float e = inb ? __fadd_rn(__uint2float_rn(sad), __fmul_rn(a.lm, S[i])) : FLT_MAX;
+    const float e = inb[i] ? __fadd_rn(__uint2float_rn(sadv[i]), __fmul_rn(a.lm, S[i])) : FLT_MAX;
     if (i == 0) {
       best = e;
     } else {
@@ -608,7 +664,7 @@ __device__ __forceinline__ short2 reg_eval_small(const RegArgs& a, int pair, con
 // windows at once; the partial SADs are reduce-scattered inside the team so that lane i holds candidate i's SAD, computes
 // that candidate's smoothness and energy, and a shuffle argmin leaves every lane of the team with the same winner.
 template <int TEAM>
-__device__ __forceinline__ short2 reg_eval_team(const RegArgs& a, int pair, const short2* __restrict__ O,
+__device__ __forceinline__ short2 reg_eval_team(const RegArgs& a, int pair, const short2* O,
                                                 const short2* P, int bx, int by, int tl, uint32_t team_mask) {
   const int gw = a.gw, gh = a.gh, bs = a.bs;
   const int idx = by * gw + bx;
@@ -632,14 +688,23 @@ __device__ __forceinline__ short2 reg_eval_team(const RegArgs& a, int pair, cons
   const uint8_t* blk = a.i1.p + (size_t)pair * a.i1.plane + (size_t)y * pitch + x;
   const uint8_t* ref = a.i2.p + (size_t)pair * a.i2.plane;
   // candidate windows: out-of-image ones (:578-582) read the block's own position and get FLT_MAX below
+  // Only the first slot of every distinct vector loads its window ("need", team-uniform; a listed block has 2.3
+  // distinct vectors among its nine candidates on average); the other slots copy the partial sums below.
   uint32_t inb = 0;
   const uint8_t* bp[9];
+  uint32_t pk[9];
+  bool need[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) {
+    pk[i] = pack_mv(c[i]);
     const int px = x + c[i].x, py = y + c[i].y;
     const bool ok = (unsigned)px <= (unsigned)(w - bs) && (unsigned)py <= (unsigned)(h - bs);
     inb |= ok ? (1u << i) : 0u;
-    bp[i] = ref + (size_t)(ok ? py : y) * pitch + (ok ? px : x);
+    bool dup = false;
+#pragma unroll
+    for (int j = 0; j < i; ++j) dup = dup || pk[j] == pk[i];
+    need[i] = ok && !dup;
+    bp[i] = ref + (size_t)(need[i] ? py : y) * pitch + (need[i] ? px : x);
   }
   // Partial SADs of this lane's rows.  A window row starts at any byte: it is fetched as the two aligned 16-byte (8x8
   // blocks: 8-byte) vectors that contain it -- two requests per row instead of five (three) 32-bit ones; a team's lanes
@@ -658,8 +723,8 @@ __device__ __forceinline__ short2 reg_eval_team(const RegArgs& a, int pair, cons
       const uintptr_t ab = reinterpret_cast<uintptr_t>(bp[i] + ro);
       const uint2* q = reinterpret_cast<const uint2*>(ab & ~(uintptr_t)7);
       off[i] = (uint32_t)(ab & 7);
-      q0[i] = __ldg(q);
-      q1[i] = __ldg(q + 1);
+      q0[i] = need[i] ? __ldg(q) : make_uint2(0u, 0u);
+      q1[i] = need[i] ? __ldg(q + 1) : make_uint2(0u, 0u);
     }
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
@@ -683,8 +748,8 @@ __device__ __forceinline__ short2 reg_eval_team(const RegArgs& a, int pair, cons
           const uintptr_t ab = reinterpret_cast<uintptr_t>(bp[i] + ro);
           const uint4* q = reinterpret_cast<const uint4*>(ab & ~(uintptr_t)15);
           off[i] = (uint32_t)(ab & 15);
-          q0[i] = __ldg(q);
-          q1[i] = __ldg(q + 1);
+          q0[i] = need[i] ? __ldg(q) : make_uint4(0u, 0u, 0u, 0u);
+          q1[i] = need[i] ? __ldg(q + 1) : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
@@ -705,6 +770,12 @@ __device__ __forceinline__ short2 reg_eval_team(const RegArgs& a, int pair, cons
     }
   }
 
+  // slots that share a vector share the partial sums
+#pragma unroll
+  for (int i = 1; i < 9; ++i) {
+#pragma unroll
+    for (int j = 0; j < i; ++j) v[i] = (pk[j] == pk[i]) ? v[j] : v[i];
+  }
   // Reduce-scatter inside the team: the nine sums live in 16 slots; at each step a lane keeps one half of its slots and
   // hands the other half to its partner, so that lane i (8x8 teams: lane i / 2) ends with the team total of candidate i
   // -- 15 (14) shuffles instead of 9 * log2(TEAM).  32-lane teams first fold their two halves together.
@@ -732,11 +803,9 @@ __device__ __forceinline__ short2 reg_eval_team(const RegArgs& a, int pair, cons
   // |c_k.y - c_i.y| (:637-641) in float like the reference (integer-valued, < 2^24, exact; FADD with |.| modifiers on the
   // FMA pipe); all nine slots are summed and the missing slots' share removed (each holds a copy of C, i.e. d(i, 0)).
   // Before, every lane of a team repeated all 36 pair distances.
-  uint32_t pk[9];
   float fx[9], fy[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) {
-    pk[i] = pack_mv(c[i]);
     fx[i] = (float)c[i].x;
     fy[i] = (float)c[i].y;
   }
@@ -784,7 +853,7 @@ __device__ __forceinline__ short2 reg_eval_team(const RegArgs& a, int pair, cons
 
 // TEAM == 1 evaluates 2x2 blocks, TEAM == 2 is the tag for "one thread per 4x4 block" (TEAMSZ below is 1 for both)
 template <int TEAM>
-__device__ __forceinline__ short2 reg_eval_any(const RegArgs& a, int pair, const short2* __restrict__ O, const short2* P,
+__device__ __forceinline__ short2 reg_eval_any(const RegArgs& a, int pair, const short2* O, const short2* P,
                                                int bx, int by, int tl, uint32_t team_mask, bool live) {
   if (TEAM == 1) {
     return reg_eval_small<2>(a, pair, O, P, bx, by, live);
@@ -1108,6 +1177,582 @@ void launch_reg_fix(const RegArgs& a, int r0, int n, cudaStream_t s) {
     case 2: k_reg_fix<2><<<n, 512, 0, s>>>(a, r0); break;
     default: k_reg_fix<1><<<n, 512, 0, s>>>(a, r0); break;
   }
+}
+
+// ============================================================================================ lean evaluators
+// What the evaluators above cost is instructions, not bytes: 1300-1600 per lane and evaluation (nine-slot select chains,
+// 36 pair distances, every lane of a team repeating all of it) at 16 warps per SM.  A listed block, however, sits on the
+// border between two or three motion layers: its nine candidates hold 2.0-2.6 DISTINCT vectors on average (4 at most
+// stages' worst).  The evaluators below work on the distinct vectors.  Same arithmetic per candidate as the reference
+// (motion_framework.cpp:578-582,605-607,637-641,653-659), hence the same field; only who computes what changes.
+
+__device__ __forceinline__ int mv_x(uint32_t pk) { return (int)(short)(pk & 0xffffu); }
+__device__ __forceinline__ int mv_y(uint32_t pk) { return (int)(short)(pk >> 16); }
+
+// SAD of a 2x2 / 4x4 block of image 1 (rows in A) against the window at `b` (any alignment) of image 2
+template <int BS>
+__device__ __forceinline__ uint32_t sad_small(const uint32_t* A, const uint8_t* b, int pitch) {
+  const uintptr_t ab = reinterpret_cast<uintptr_t>(b);
+  const uint32_t sh = (uint32_t)(ab & 3);
+  const uint8_t* q = reinterpret_cast<const uint8_t*>(ab & ~(uintptr_t)3);
+  if (BS == 2) {
+    uint32_t w0[2], w1[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const uint32_t* qr = reinterpret_cast<const uint32_t*>(q + (size_t)r * pitch);
+      w0[r] = __ldg(qr);
+      w1[r] = sh == 3u ? __ldg(qr + 1) : 0u;
+    }
+    const uint32_t r0 = __funnelshift_r(w0[0], w1[0], sh * 8u) & 0xffffu;
+    const uint32_t r1 = __funnelshift_r(w0[1], w1[1], sh * 8u) & 0xffffu;
+    return sad4(A[0], r0 | (r1 << 16), 0u);
+  } else {
+    uint32_t w0[4], w1[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const uint32_t* qr = reinterpret_cast<const uint32_t*>(q + (size_t)r * pitch);
+      w0[r] = __ldg(qr);
+      w1[r] = sh != 0u ? __ldg(qr + 1) : 0u;
+    }
+    uint32_t sad = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) sad = sad4(A[r % (BS == 2 ? 1 : 4)], __funnelshift_r(w0[r], w1[r], sh * 8u), sad);
+    return sad;
+  }
+}
+
+// One thread per 2x2 / 4x4 block, blocks whose candidates hold at most two distinct vectors A (the block's own, index 0)
+// and B: S_A = (#B) * d(A, B), S_B = (#A) * d(A, B) (integer-valued, exact in float like the reference's running sum),
+// B wins iff E_B < E_A (strict: index 0 wins ties, :653-659).  Returns false if there are more than two distinct vectors
+// (the caller defers the block to the nine-slot evaluator); *out = the block's new vector otherwise.
+template <int BS>
+__device__ __forceinline__ bool reg_eval_small_fast(const RegArgs& a, int pair, const short2* O, const short2* P, int bx, int by,
+                                                    uint32_t* out) {
+  const int gw = a.gw, gh = a.gh;
+  const int idx = by * gw + bx;
+  const bool up = by > 0, dn = by < gh - 1, lf = bx > 0, rt = bx < gw - 1;
+  const uint32_t* Ou = reinterpret_cast<const uint32_t*>(O);
+  const uint32_t* Pu = reinterpret_cast<const uint32_t*>(P);
+  const uint32_t A0 = Ou[idx];
+  uint32_t pk[8];  // slots 1..8: L, R, DR, UL, UR, U, D, DL; a missing neighbour holds A and drops out below
+  pk[0] = lf ? Pu[idx - 1] : A0;
+  pk[1] = rt ? Ou[idx + 1] : A0;
+  pk[2] = (dn && rt) ? Ou[idx + gw + 1] : A0;
+  pk[3] = (up && lf) ? Pu[idx - gw - 1] : A0;
+  pk[4] = (up && rt) ? Pu[idx - gw + 1] : A0;
+  pk[5] = up ? Pu[idx - gw] : A0;
+  pk[6] = dn ? Ou[idx + gw] : A0;
+  pk[7] = (dn && lf) ? Ou[idx + gw - 1] : A0;
+  uint32_t B = A0;
+#pragma unroll
+  for (int i = 7; i >= 0; --i) B = (pk[i] != A0) ? pk[i] : B;  // the lowest slot that differs
+  *out = A0;
+  if (B == A0) return true;  // all candidates identical: index 0 wins
+  int nB = 0;
+  bool more = false;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    nB += (pk[i] == B) ? 1 : 0;
+    more = more || (pk[i] != A0 && pk[i] != B);
+  }
+  if (more) return false;
+  const int n_valid = 1 + (lf ? 1 : 0) + (rt ? 1 : 0) + ((dn && rt) ? 1 : 0) + ((up && lf) ? 1 : 0) + ((up && rt) ? 1 : 0) +
+                      (up ? 1 : 0) + (dn ? 1 : 0) + ((dn && lf) ? 1 : 0);
+  const int nA = n_valid - nB;
+  const int ax = mv_x(A0), ay = mv_y(A0), bxv = mv_x(B), byv = mv_y(B);
+  const int d = abs(ax - bxv) + abs(ay - byv);
+  const float SA = (float)(nB * d), SB = (float)(nA * d);
+  const int x = bx * BS, y = by * BS;
+  const int w = a.i1.w, h = a.i1.h, pitch = a.i1.pitch;
+  const uint8_t* blk = a.i1.p + (size_t)pair * a.i1.plane + (size_t)y * pitch + x;
+  const uint8_t* ref = a.i2.p + (size_t)pair * a.i2.plane;
+  uint32_t Ab[BS == 2 ? 1 : 4];
+  if (BS == 2) {
+    Ab[0] = (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(blk)) | ((uint32_t)__ldg(reinterpret_cast<const uint16_t*>(blk + pitch)) << 16);
+  } else {
+#pragma unroll
+    for (int r = 0; r < (BS == 2 ? 1 : 4); ++r) Ab[r] = __ldg(reinterpret_cast<const uint32_t*>(blk + (size_t)r * pitch));
+  }
+  const int pax = x + ax, pay = y + ay, pbx = x + bxv, pby = y + byv;
+  const bool inA = (unsigned)pax <= (unsigned)(w - BS) && (unsigned)pay <= (unsigned)(h - BS);  // :578
+  const bool inB = (unsigned)pbx <= (unsigned)(w - BS) && (unsigned)pby <= (unsigned)(h - BS);
+  // out-of-image candidates read the block's own position (a valid address) and get FLT_MAX
+  const uint32_t sadA = sad_small<BS>(Ab, ref + (size_t)(inA ? pay : y) * pitch + (inA ? pax : x), pitch);
+  const uint32_t sadB = sad_small<BS>(Ab, ref + (size_t)(inB ? pby : y) * pitch + (inB ? pbx : x), pitch);
+  const float EA = inA ? __fadd_rn(__uint2float_rn(sadA), __fmul_rn(a.lm, SA)) : FLT_MAX;
+  const float EB = inB ? __fadd_rn(__uint2float_rn(sadB), __fmul_rn(a.lm, SB)) : FLT_MAX;
+  *out = (EB < EA) ? B : A0;
+  return true;
+}
+
+// partial SAD of this lane's share of one candidate window.  BSK == 8: row `row` (8 bytes) of an 8x8 block; BSK == 16: row
+// `row` of a 16x16 block; BSK == 32: rows row, row + 32, ... of a block of 32 or more, in 16-byte chunks.  Windows start at
+// any byte: a row is fetched as the two aligned vectors that contain it and the wanted words are selected by the start
+// offset before the byte shift (two requests per row instead of three or five 32-bit ones).
+template <int BSK>
+__device__ __forceinline__ uint32_t team_partial_sad(const uint8_t* blk, const uint8_t* win, int pitch, int bs, int row) {
+  uint32_t sum = 0;
+  if (BSK == 8) {
+    const size_t ro = (size_t)row * pitch;
+    const uint2 A = __ldg(reinterpret_cast<const uint2*>(blk + ro));
+    const uintptr_t ab = reinterpret_cast<uintptr_t>(win + ro);
+    const uint2* q = reinterpret_cast<const uint2*>(ab & ~(uintptr_t)7);
+    const uint32_t off = (uint32_t)(ab & 7);
+    const uint2 q0 = __ldg(q), q1 = __ldg(q + 1);
+    const bool w1 = (off & 4u) != 0u;
+    const uint32_t sh = (off & 3u) * 8u;
+    const uint32_t a0 = w1 ? q0.y : q0.x, a1 = w1 ? q1.x : q0.y, a2 = w1 ? q1.y : q1.x;
+    sum = sad4(A.y, __funnelshift_r(a1, a2, sh), sad4(A.x, __funnelshift_r(a0, a1, sh), 0u));
+  } else {
+    const int rows = BSK == 16 ? 1 : bs / 32;
+    const int chunks = BSK == 16 ? 1 : bs / 16;
+    for (int rr = 0; rr < rows; ++rr) {
+      for (int ch = 0; ch < chunks; ++ch) {
+        const size_t ro = (size_t)(rr * 32 + row) * pitch + ch * 16;
+        const uint4 A = __ldg(reinterpret_cast<const uint4*>(blk + ro));
+        const uintptr_t ab = reinterpret_cast<uintptr_t>(win + ro);
+        const uint4* q = reinterpret_cast<const uint4*>(ab & ~(uintptr_t)15);
+        const uint32_t off = (uint32_t)(ab & 15);
+        const uint4 q0 = __ldg(q), q1 = __ldg(q + 1);
+        const bool s2 = (off & 8u) != 0u, s1 = (off & 4u) != 0u;
+        const uint32_t sh = (off & 3u) * 8u;
+        const uint32_t t0 = s2 ? q0.z : q0.x, t1 = s2 ? q0.w : q0.y, t2 = s2 ? q1.x : q0.z, t3 = s2 ? q1.y : q0.w,
+                       t4 = s2 ? q1.z : q1.x, t5 = s2 ? q1.w : q1.y;
+        const uint32_t a0 = s1 ? t1 : t0, a1 = s1 ? t2 : t1, a2 = s1 ? t3 : t2, a3 = s1 ? t4 : t3, a4 = s1 ? t5 : t4;
+        sum = sad4(A.x, __funnelshift_r(a0, a1, sh), sum);
+        sum = sad4(A.y, __funnelshift_r(a1, a2, sh), sum);
+        sum = sad4(A.z, __funnelshift_r(a2, a3, sh), sum);
+        sum = sad4(A.w, __funnelshift_r(a3, a4, sh), sum);
+      }
+    }
+  }
+  return sum;
+}
+
+// Blocks of 8x8 and larger, a team of adjacent lanes per block (16 lanes for 8x8 and 16x16 blocks, 32 above; whole warps call
+// this together).  Lane s < 9 of a team OWNS candidate slot s: it loads that one vector, finds out whether an earlier slot
+// holds the same one (match.any), sums its smoothness over the other lanes' vectors and ends with its energy.  The windows of
+// the DISTINCT in-image vectors (a team-uniform list) are summed row-wise by all lanes, several per memory round trip
+// (16x16 and up: three windows, one row each; 8x8: four windows, each half of the team takes two); a shuffle argmin over
+// (energy, slot) gives every lane the winner.  ~300 instructions per lane instead of ~1600.
+template <int BSK>  // 8, 16, or 32 (= 32 and larger)
+__device__ __forceinline__ uint32_t reg_eval_team_lean(const RegArgs& a, int pair, const short2* O, const short2* P, int bx,
+                                                       int by, int tl, bool live) {
+  constexpr int TEAMSZ = BSK >= 32 ? 32 : 16;
+  constexpr uint32_t FULL = 0xffffffffu;
+  const int gw = a.gw, gh = a.gh, bs = a.bs;
+  const int lane = threadIdx.x & 31;
+  const int base = lane - tl;  // first lane of this team inside the warp
+  const int idx = by * gw + bx;
+  // slot -> neighbour: [C, L, R, DR, UL, UR, U, D, DL] (:441-449); L, UL, UR, U come from the new field
+  const int s = tl < 9 ? tl : 0;
+  const int ddx = (s == 2 || s == 3 || s == 5) ? 1 : ((s == 1 || s == 4 || s == 8) ? -1 : 0);
+  const int ddy = (s == 3 || s == 7 || s == 8) ? 1 : ((s == 4 || s == 5 || s == 6) ? -1 : 0);
+  const bool from_new = s == 1 || s == 4 || s == 5 || s == 6;
+  const int nx = bx + ddx, ny = by + ddy;
+  const bool valid = tl < 9 && nx >= 0 && nx < gw && ny >= 0 && ny < gh;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(from_new ? P : O);
+  uint32_t my = src[valid ? idx + ddy * gw + ddx : idx];
+  const uint32_t c0 = __shfl_sync(FULL, my, base);  // slot 0 is always valid and reads O
+  if (!valid) my = c0;
+  // first slot of the team that holds my vector (invalid slots hold C's, i.e. slot 0's)
+  const uint32_t same = __match_any_sync(FULL, my) & (0x1ffu << base);
+  const int first = __ffs(same) - 1 - base;
+  const int x = bx * bs, y = by * bs;
+  const int w = a.i1.w, h = a.i1.h, pitch = a.i1.pitch;
+  const int mx = mv_x(my), myy = mv_y(my);
+  const bool inb = (unsigned)(x + mx) <= (unsigned)(w - bs) && (unsigned)(y + myy) <= (unsigned)(h - bs);  // :578
+  const uint32_t valid_mask = (__ballot_sync(FULL, valid) >> base) & 0x1ffu;
+  uint32_t need_mask = (__ballot_sync(FULL, live && valid && inb && first == tl) >> base) & 0x1ffu;
+  // smoothness of my slot over all gathered candidates (:637-641): integer-valued, exact in float like the running sum
+  int S = 0;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const uint32_t vk = __shfl_sync(FULL, my, base + k);
+    const int dk = abs(mx - mv_x(vk)) + abs(myy - mv_y(vk));
+    S += ((valid_mask >> k) & 1u) ? dk : 0;
+  }
+  const uint8_t* blk = a.i1.p + (size_t)pair * a.i1.plane + (size_t)y * pitch + x;
+  const uint8_t* ref = a.i2.p + (size_t)pair * a.i2.plane;
+  uint32_t mysad = 0;
+  if (BSK == 8) {
+    // four windows per round trip: half hf of the team sums windows j[hf] and j[2 + hf], one row per lane
+    const int hf = tl >> 3, row = tl & 7;
+    const int batches = __reduce_max_sync(FULL, (unsigned)((__popc(need_mask) + 3) / 4));
+    for (int it = 0; it < batches; ++it) {
+      int j[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        j[q] = need_mask ? __ffs(need_mask) - 1 : -1;
+        need_mask &= need_mask - 1u;
+      }
+      uint32_t part[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int jj = hf ? j[2 * q + 1] : j[2 * q];
+        const uint32_t vj = __shfl_sync(FULL, my, base + (jj >= 0 ? jj : 0));
+        part[q] = 0;
+        if (jj >= 0) part[q] = team_partial_sad<8>(blk, ref + (size_t)(y + mv_y(vj)) * pitch + (x + mv_x(vj)), pitch, bs, row);
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+#pragma unroll
+        for (int o = 4; o >= 1; o >>= 1) part[q] += __shfl_xor_sync(FULL, part[q], o);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {  // window j[c] was summed by half (c & 1) as its part[c >> 1]
+        const uint32_t tot = __shfl_sync(FULL, part[c >> 1], base + 8 * (c & 1));
+        mysad = (j[c] >= 0 && first == j[c]) ? tot : mysad;
+      }
+    }
+  } else {
+    const int batches = __reduce_max_sync(FULL, (unsigned)((__popc(need_mask) + 2) / 3));
+    for (int it = 0; it < batches; ++it) {
+      int j[3];
+      uint32_t part[3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        j[q] = need_mask ? __ffs(need_mask) - 1 : -1;
+        need_mask &= need_mask - 1u;
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const uint32_t vj = __shfl_sync(FULL, my, base + (j[q] >= 0 ? j[q] : 0));
+        part[q] = 0;
+        if (j[q] >= 0) part[q] = team_partial_sad<BSK>(blk, ref + (size_t)(y + mv_y(vj)) * pitch + (x + mv_x(vj)), pitch, bs, tl);
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+#pragma unroll
+        for (int o = TEAMSZ / 2; o >= 1; o >>= 1) part[q] += __shfl_xor_sync(FULL, part[q], o);
+        mysad = (j[q] >= 0 && first == j[q]) ? part[q] : mysad;
+      }
+    }
+  }
+  // (:607) un-fused; (:578-582) FLT_MAX outside the image; slots without a neighbour can never win
+  float e = (valid && inb) ? __fadd_rn(__uint2float_rn(mysad), __fmul_rn(a.lm, (float)S)) : FLT_MAX;
+  int bi = valid ? tl : 15;
+  // argmin over the team: smallest energy, ties to the smallest slot == the reference's scan with strict '<' (:653-659);
+  // slot 0 (C) is always present, so an all-FLT_MAX block keeps its vector
+#pragma unroll
+  for (int o = TEAMSZ / 2; o >= 1; o >>= 1) {
+    const float oe = __shfl_xor_sync(FULL, e, o);
+    const int oi = __shfl_xor_sync(FULL, bi, o);
+    const bool take = oe < e || (oe == e && oi < bi);
+    e = take ? oe : e;
+    bi = take ? oi : bi;
+  }
+  return __shfl_sync(FULL, my, base + (bi < 9 ? bi : 0));
+}
+
+// ============================================================================================ fused level schedule
+// The whole regularisation schedule of one pyramid level (motion_framework.cpp:133-154: for every block size from the
+// level's initial one down to 2, `sweeps` sweeps with lambda_multiplier 1..sweeps, then divide_blocks, lambda *= 2) in ONE
+// launch: a cluster of CS CTAs owns a frame pair and walks through classify -> evaluation rounds -> next sweep -> split with
+// cluster barriers only.  What the per-sweep launches of round 1 lost is gone: ~30 dependent launches per level (each at
+// least a few microseconds, i.e. most of a single pair's latency), and a kernel boundary per phase at which every pair of a
+// chunk waited for the slowest one (now a pair's cluster runs ahead on its own; pairs only meet at the end of the level).
+// Large chunks run CS = 1 (one CTA per pair, plain __syncthreads, counters in shared memory), small chunks spread a pair
+// over up to 8 SMs (barrier.cluster, counters in the DSMEM of rank 0; the barrier also invalidates the L1, so fields
+// written by a sibling CTA are re-read from the L2).
+//
+// A sweep is the same fixed-point iteration as before, with one change: the first pass over the listed blocks already reads
+// its "pred" neighbours from the NEW field (chaotic iteration from the start; a block that read a stale value is
+// re-enqueued by the neighbour that changed, so the unique fixed point -- the reference's in-place raster result -- is
+// reached whatever the interleaving), which shortens the tail because the list is in raster order.
+namespace cg = cooperative_groups;
+
+struct LevelCtx {
+  uint32_t* cnt;     // three rotating list counters + two alternating counters of the deferred list (shared memory of rank 0)
+  int rank, cs;
+  uint32_t gtid, gthreads;
+};
+
+template <bool MULTI>
+__device__ __forceinline__ void level_sync() {
+  if (MULTI) cg::this_cluster().sync();
+  else __syncthreads();
+}
+
+// classify: copy O -> Y, list the blocks whose nine gathered candidates are not all identical (see k_reg_classify4)
+__device__ __forceinline__ void level_classify(const RegArgs& a, int pair, const LevelCtx& lc, uint32_t* list) {
+  const int gw = a.gw, gh = a.gh;
+  // no __restrict__ / read-only loads on the fields: the two buffers swap roles from sweep to sweep inside one launch
+  const uint32_t* O = reinterpret_cast<const uint32_t*>(a.O + (size_t)pair * a.mv_plane);
+  uint32_t* Y = reinterpret_cast<uint32_t*>(a.Y + (size_t)pair * a.mv_plane);
+  const int lane = threadIdx.x & 31;
+  if ((gw & 3) == 0 && (a.mv_plane & 3) == 0) {
+    const int gw4 = gw >> 2;
+    const uint32_t groups = (uint32_t)gw4 * gh;
+    const uint32_t limit = (groups + 31u) / 32u * 32u;
+    for (uint32_t t = lc.gtid; t < limit; t += lc.gthreads) {
+      uint32_t work = 0;
+      int i0 = 0;
+      if (t < groups) {
+        const int by = (int)(t / gw4), bx = (int)(t - (uint32_t)by * gw4) * 4;
+        i0 = by * gw + bx;
+        const int ru = max(by - 1, 0) * gw, rm = by * gw, rd = min(by + 1, gh - 1) * gw;
+        const int cl = max(bx - 1, 0), cr = min(bx + 4, gw - 1);
+        const uint4 U = *reinterpret_cast<const uint4*>(O + ru + bx);
+        const uint4 M = *reinterpret_cast<const uint4*>(O + rm + bx);
+        const uint4 D = *reinterpret_cast<const uint4*>(O + rd + bx);
+        const uint32_t u[6] = {O[ru + cl], U.x, U.y, U.z, U.w, O[ru + cr]};
+        const uint32_t m[6] = {O[rm + cl], M.x, M.y, M.z, M.w, O[rm + cr]};
+        const uint32_t d[6] = {O[rd + cl], D.x, D.y, D.z, D.w, O[rd + cr]};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t k0 = m[j + 1];
+          const bool same = u[j] == k0 && u[j + 1] == k0 && u[j + 2] == k0 && m[j] == k0 && m[j + 2] == k0 && d[j] == k0 &&
+                            d[j + 1] == k0 && d[j + 2] == k0;
+          work |= same ? 0u : (1u << j);
+        }
+        *reinterpret_cast<uint4*>(Y + i0) = M;
+      }
+      const int k = __popc(work);
+      if (__ballot_sync(0xffffffffu, k > 0) == 0u) continue;
+      int incl = k;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      uint32_t base = 0;
+      if (lane == 31) base = atomicAdd(&lc.cnt[0], (uint32_t)incl);
+      base = __shfl_sync(0xffffffffu, base, 31);
+      uint32_t* dst = list + base + (uint32_t)(incl - k);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if ((work >> j) & 1u) *dst++ = (uint32_t)(i0 + j);
+    }
+  } else {
+    const uint32_t nb = (uint32_t)gw * gh;
+    const uint32_t limit = (nb + 31u) / 32u * 32u;
+    for (uint32_t t = lc.gtid; t < limit; t += lc.gthreads) {
+      bool work = false;
+      if (t < nb) {
+        const int by = (int)(t / gw), bx = (int)(t - (uint32_t)by * gw);
+        const int ru = max(by - 1, 0) * gw, rm = by * gw, rd = min(by + 1, gh - 1) * gw;
+        const int cl = max(bx - 1, 0), cr = min(bx + 1, gw - 1);
+        const uint32_t k0 = O[t];
+        const uint32_t v[8] = {O[ru + cl], O[ru + bx], O[ru + cr], O[rm + cl], O[rm + cr], O[rd + cl], O[rd + bx], O[rd + cr]};
+        bool same = true;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) same = same && v[j] == k0;
+        Y[t] = k0;
+        work = !same;
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, work);
+      if (m) {
+        const int leader = __ffs(m) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&lc.cnt[0], (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (work) list[base + __popc(m & ((1u << lane) - 1u))] = t;
+      }
+    }
+  }
+}
+
+// One sweep at the current block size: classify, then rounds until the work list is empty.
+// BSK: 2 / 4 = one thread per block (two-vector fast path, the rest deferred to the nine-slot evaluator in a second pass of
+// the same round), 8 / 16 / 32 = lean team evaluator (16 / 16 / 32 lanes per block).
+template <int BSK, bool MULTI>
+__device__ __forceinline__ void level_sweep(const RegArgs& a, int pair, const LevelCtx& lc, uint32_t& ep, uint32_t& rounds,
+                                            uint32_t& blocks) {
+  constexpr int TEAMSZ = BSK <= 4 ? 1 : (BSK >= 32 ? 32 : 16);
+  constexpr int TPW = 32 / TEAMSZ;
+  const short2* O = a.O + (size_t)pair * a.mv_plane;
+  short2* Y = a.Y + (size_t)pair * a.mv_plane;
+  uint32_t* Yu = reinterpret_cast<uint32_t*>(Y);
+  uint32_t* stamp = a.stamp + (size_t)pair * a.wl_plane;
+  uint32_t* lists[2] = {a.list0 + (size_t)pair * a.wl_plane, a.list1 + (size_t)pair * a.wl_plane};
+  uint32_t* dlist = reinterpret_cast<uint32_t*>(a.nv) + (size_t)pair * a.wl_plane;  // blocks deferred to the nine-slot evaluator
+  const int lane = threadIdx.x & 31;
+  if (lc.gtid == 0) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) lc.cnt[i] = 0;
+  }
+  level_sync<MULTI>();
+  level_classify(a, pair, lc, lists[0]);
+  level_sync<MULTI>();
+  const uint32_t team = lc.gtid / TEAMSZ, tl = lc.gtid % TEAMSZ, nteams = lc.gthreads / TEAMSZ;
+  for (int r = 0;; ++r) {
+    // round r reads list[r & 1] (counter r % 3), appends to list[(r + 1) & 1] (counter (r + 1) % 3) and clears counter
+    // (r + 2) % 3, which was last read before the barrier that precedes this round; the deferred list's counter alternates
+    // between words 3 and 4 for the same reason
+    const uint32_t cnt = *reinterpret_cast<volatile uint32_t*>(&lc.cnt[r % 3]);
+    if (cnt == 0) break;
+    if (lc.gtid == 0) {
+      lc.cnt[(r + 2) % 3] = 0;
+      lc.cnt[3 + ((r + 1) & 1)] = 0;
+    }
+    const uint32_t* lcur = lists[r & 1];
+    uint32_t* lnext = lists[(r + 1) & 1];
+    uint32_t* next_count = &lc.cnt[(r + 1) % 3];
+    uint32_t* dcount = &lc.cnt[3 + (r & 1)];
+    ++ep;
+    const uint32_t limit = (cnt + TPW - 1) / TPW * TPW;  // whole warps iterate together
+    for (uint32_t e = team; e < limit; e += nteams) {
+      const bool live = e < cnt;
+      const int b = (int)lcur[live ? e : cnt - 1];
+      const int bx = b % a.gw, by = b / a.gw;
+      uint32_t nv = 0;
+      bool changed;
+      if (BSK <= 4) {
+        const bool done = !live || reg_eval_small_fast<BSK>(a, pair, O, Y, bx, by, &nv);
+        const uint32_t dm = __ballot_sync(0xffffffffu, !done);
+        if (dm) {
+          uint32_t dbase = 0;
+          const int leader = __ffs(dm) - 1;
+          if (lane == leader) dbase = atomicAdd(dcount, (uint32_t)__popc(dm));
+          dbase = __shfl_sync(0xffffffffu, dbase, leader);
+          if (!done) dlist[dbase + __popc(dm & ((1u << lane) - 1u))] = (uint32_t)b;
+        }
+        changed = live && done && nv != Yu[b];
+      } else {
+        nv = reg_eval_team_lean<BSK>(a, pair, O, Y, bx, by, (int)tl, live);
+        changed = tl == 0 && live && nv != Yu[b];
+      }
+      if (changed) Yu[b] = nv;
+      push_dependents(changed, bx, by, a.gw, a.gh, stamp, ep, lnext, next_count);
+    }
+    if (BSK <= 4) {
+      // second pass of the round: the blocks with three or more distinct candidate vectors
+      if (MULTI) __threadfence();
+      level_sync<MULTI>();
+      const uint32_t dcnt = *reinterpret_cast<volatile uint32_t*>(dcount);
+      const uint32_t dlimit = (dcnt + 31u) / 32u * 32u;
+      for (uint32_t e = lc.gtid; e < dlimit; e += lc.gthreads) {
+        const bool live = e < dcnt;
+        const int b = (int)dlist[live ? e : dcnt - 1];
+        const int bx = b % a.gw, by = b / a.gw;
+        const short2 nv2 = reg_eval_small<BSK == 2 ? 2 : 4>(a, pair, O, Y, bx, by, live);
+        const bool changed = live && pack_mv(nv2) != Yu[b];
+        if (changed) Y[b] = nv2;
+        push_dependents(changed, bx, by, a.gw, a.gh, stamp, ep, lnext, next_count);
+      }
+    }
+    if (r > 0) {  // the first pass is the sweep itself; later rounds are the fix-up
+      rounds += 1;
+      blocks += cnt;
+    }
+    if (MULTI) __threadfence();
+    level_sync<MULTI>();
+  }
+}
+
+template <bool MULTI>
+__global__ void __launch_bounds__(512, 1) k_reg_level(RegArgs a, int sweeps, float lambda0, int first_mult, int single_stage) {
+  __shared__ uint32_t s_cnt[8];
+  LevelCtx lc;
+  int pair;
+  if (MULTI) {
+    cg::cluster_group cl = cg::this_cluster();
+    lc.cs = (int)cl.num_blocks();
+    lc.rank = (int)cl.block_rank();
+    lc.cnt = cl.map_shared_rank(s_cnt, 0);
+    pair = blockIdx.x / lc.cs;
+  } else {
+    lc.cs = 1;
+    lc.rank = 0;
+    lc.cnt = s_cnt;
+    pair = blockIdx.x;
+  }
+  lc.gtid = (uint32_t)lc.rank * blockDim.x + threadIdx.x;
+  lc.gthreads = (uint32_t)lc.cs * blockDim.x;
+  uint32_t* ctr = a.ctr + (size_t)pair * kCtrWords;
+  uint32_t ep = ctr[CTR_EPOCH];
+  if (ep > 0xf0000000u) {  // the de-duplication stamps must stay below every epoch still to come: restart before a wrap
+    uint32_t* stamp = a.stamp + (size_t)pair * a.wl_plane;
+    for (size_t i = lc.gtid; i < a.wl_plane; i += lc.gthreads) stamp[i] = 0u;
+    ep = 0;
+    if (MULTI) __threadfence();
+  }
+  level_sync<MULTI>();
+  uint32_t rounds = 0, blocks = 0;
+  float lambda = lambda0;
+  for (int g = a.bs; g > 1; g >>= 1) {
+    for (int sw = first_mult; sw < first_mult + sweeps; ++sw) {
+      a.lm = lambda * (float)sw;  // lambda * (float)lambda_multiplier, motion_framework.cpp:607
+      switch (g >= 32 ? 32 : g) {
+        case 32: level_sweep<32, MULTI>(a, pair, lc, ep, rounds, blocks); break;
+        case 16: level_sweep<16, MULTI>(a, pair, lc, ep, rounds, blocks); break;
+        case 8: level_sweep<8, MULTI>(a, pair, lc, ep, rounds, blocks); break;
+        case 4: level_sweep<4, MULTI>(a, pair, lc, ep, rounds, blocks); break;
+        default: level_sweep<2, MULTI>(a, pair, lc, ep, rounds, blocks); break;
+      }
+      const short2* t = a.O; a.O = a.Y; a.Y = const_cast<short2*>(t);
+    }
+    if (single_stage) break;
+    if (g > 2) {
+      // MF::divide_blocks (motion_framework.cpp:845-862): a.O (gw x gh) -> a.Y (2gw x 2gh)
+      const uint32_t* in = reinterpret_cast<const uint32_t*>(a.O + (size_t)pair * a.mv_plane);
+      uint32_t* out = reinterpret_cast<uint32_t*>(a.Y + (size_t)pair * a.mv_plane);
+      const int gw = a.gw, gh = a.gh;
+      if ((gw & 1) == 0 && (a.mv_plane & 3) == 0) {
+        const int hw = gw >> 1;
+        for (uint32_t i = lc.gtid; i < (uint32_t)hw * gh; i += lc.gthreads) {
+          const int y = (int)(i / hw), x2 = (int)(i - (uint32_t)y * hw);
+          const uint2 v = *reinterpret_cast<const uint2*>(in + (size_t)y * gw + 2 * x2);
+          const uint4 o = make_uint4(v.x, v.x, v.y, v.y);
+          uint32_t* dst = out + (size_t)(2 * y) * (2 * gw) + 4 * x2;
+          *reinterpret_cast<uint4*>(dst) = o;
+          *reinterpret_cast<uint4*>(dst + 2 * gw) = o;
+        }
+      } else {
+        const int ow = 2 * gw;
+        for (uint32_t i = lc.gtid; i < (uint32_t)ow * 2 * gh; i += lc.gthreads) {
+          const int y = (int)(i / ow), x = (int)(i - (uint32_t)y * ow);
+          out[i] = in[(size_t)(y >> 1) * gw + (x >> 1)];
+        }
+      }
+      const short2* t = a.O; a.O = a.Y; a.Y = const_cast<short2*>(t);
+      a.gw *= 2;
+      a.gh *= 2;
+      if (MULTI) __threadfence();
+      level_sync<MULTI>();
+    }
+    a.bs = g >> 1;
+    lambda = lambda * 2;
+  }
+  if (lc.gtid == 0) {
+    ctr[CTR_EPOCH] = ep;
+    ctr[CTR_ROUNDS] += rounds;
+    ctr[CTR_BLOCKS] += blocks;
+  }
+  // rank 0 owns the counters its siblings read through DSMEM: nobody leaves before everybody has read the final zero
+  if (MULTI) level_sync<MULTI>();
+}
+
+int launch_reg_level(const RegArgs& a, int sweeps, float lambda0, int first_mult, int single_stage, int n, int sm_count,
+                     cudaStream_t s) {
+  // cluster size: spread a pair over several SMs while the chunk leaves SMs idle
+  int cs = 1;
+  while (cs < 8 && 2 * cs * n <= sm_count) cs *= 2;
+  if (const char* e = getenv("BBME_REG_CLUSTER")) {
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4 || v == 8) cs = v;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(n * cs));
+  cfg.blockDim = dim3(512);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e;
+  if (cs == 1) {
+    k_reg_level<false><<<n, 512, 0, s>>>(a, sweeps, lambda0, first_mult, single_stage);
+    e = cudaGetLastError();
+  } else {
+    e = cudaLaunchKernelEx(&cfg, k_reg_level<true>, a, sweeps, lambda0, first_mult, single_stage);
+  }
+  return e == cudaSuccess ? 0 : -1;
 }
 
 // ============================================================================================ integer peak

@@ -69,6 +69,12 @@ void launch_reg_full(const RegArgs& a, int n, cudaStream_t s);
 // grid-wide fix-up round `r` (0-based) over all pairs; then the per-pair tail loop starting at round `r0`
 void launch_reg_round(const RegArgs& a, int r, int n, cudaStream_t s);
 void launch_reg_fix(const RegArgs& a, int r0, int n, cudaStream_t s);
+// The whole schedule of a level in one launch: a.bs / a.gw / a.gh describe the level's INITIAL block grid, a.O holds the field
+// after the search; the result ends in a.O or a.Y depending on the number of sweeps and splits (the caller tracks the
+// ping-pong like the per-sweep path does).  Returns 0 or -1 (launch failure).
+// first_mult: lambda_multiplier of the first sweep (1 in the schedule); single_stage: stop after the sweeps of a.bs.
+int launch_reg_level(const RegArgs& a, int sweeps, float lambda0, int first_mult, int single_stage, int n, int sm_count,
+                     cudaStream_t s);
 
 // VABSDIFF4 issue-rate micro-benchmark (kernels.cu); returns 0 on success
 int measure_int_peak(int sm_count, double* absdiff_per_s, double* sm_mhz);
@@ -90,7 +96,7 @@ struct TmaSearchPlan {
 // returns 0 on success; fills plan->supported
 int tma_search_plan(TmaSearchPlan* plan, const uint8_t* img1, const uint8_t* img2, int w, int h, int pitch,
                     size_t plane, int n_planes, int bs, int R, char* err, size_t errlen);
-void launch_search_tma(const TmaSearchPlan& plan, ImgView i1, ImgView i2, MvView mv, int n,
+int launch_search_tma(const TmaSearchPlan& plan, ImgView i1, ImgView i2, MvView mv, int n,
                        unsigned long long* counters, int sm_count, cudaStream_t s);
 
 }  // namespace bbme

@@ -455,14 +455,14 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static PFN_encodeTiled get_encode() {
-  static PFN_encodeTiled fn = nullptr;
-  if (!fn) {
+  static const PFN_encodeTiled fn = [] {  // initialised once, thread-safe (contexts may be planned from several host threads)
     void* p = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
         qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_encodeTiled>(p);
-  }
+      return reinterpret_cast<PFN_encodeTiled>(p);
+    return static_cast<PFN_encodeTiled>(nullptr);
+  }();
   return fn;
 }
 
@@ -583,10 +583,32 @@ static bool make_geom(int w, int h, int bs, int R, TmaGeom* g) {
   return true;
 }
 
+// One instantiation: a == nullptr prepares it (shared-memory opt-in, once per plan), else launches it.
 template <int BS, int SEG, int PWW, bool K64>
-static void launch_inst(const TmaSearchPlan& plan, const TmaSearchArgs& a, int grid, cudaStream_t s) {
-  cudaFuncSetAttribute(k_search_tma<BS, SEG, PWW, K64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  k_search_tma<BS, SEG, PWW, K64><<<grid, kThreads, plan.smem_bytes, s>>>(plan.map_win, plan.map_blk, a);
+static int run_inst(const TmaSearchPlan& plan, const TmaSearchArgs* a, int grid, cudaStream_t s) {
+  if (!a)
+    return cudaFuncSetAttribute(k_search_tma<BS, SEG, PWW, K64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess ? 1 : -1;
+  k_search_tma<BS, SEG, PWW, K64><<<grid, kThreads, plan.smem_bytes, s>>>(plan.map_win, plan.map_blk, *a);
+  return 1;
+}
+
+// Finds the instantiation of (block size, rows per lane, window pitch class, key width).  Returns 1 = done, 0 = there is none
+// (the caller falls back to the generic kernel at plan time; never silently at launch time), -1 = CUDA error.
+static int dispatch(const TmaSearchPlan& plan, int k64, int pww, const TmaSearchArgs* a, int grid, cudaStream_t s) {
+#define BBME_CASE(BS_, SEG_, PWW_) \
+  if (!k64 && plan.bs == BS_ && plan.seg == SEG_ && pww == PWW_) return run_inst<BS_, SEG_, PWW_, false>(plan, a, grid, s);
+#define BBME_CASE64(BS_, SEG_, PWW_) \
+  if (k64 && plan.bs == BS_ && plan.seg == SEG_ && pww == PWW_) return run_inst<BS_, SEG_, PWW_, true>(plan, a, grid, s);
+#define BBME_CASES(BS_, SEG_) \
+  BBME_CASE(BS_, SEG_, 16) BBME_CASE(BS_, SEG_, 24) BBME_CASE(BS_, SEG_, 32) BBME_CASE(BS_, SEG_, 40) \
+  BBME_CASE(BS_, SEG_, 48) BBME_CASE(BS_, SEG_, 64)
+  BBME_CASES(8, 13) BBME_CASES(8, 11) BBME_CASES(8, 26) BBME_CASES(8, 43) BBME_CASES(16, 13) BBME_CASES(16, 11) BBME_CASES(32, 13) BBME_CASES(32, 11)
+  BBME_CASE64(16, 13, 40) BBME_CASE64(16, 13, 64) BBME_CASE64(16, 11, 40) BBME_CASE64(16, 11, 64)
+  BBME_CASE64(32, 13, 40) BBME_CASE64(32, 13, 64) BBME_CASE64(32, 11, 40) BBME_CASE64(32, 11, 64)
+#undef BBME_CASE64
+#undef BBME_CASES
+#undef BBME_CASE
+  return 0;
 }
 
 int tma_search_plan(TmaSearchPlan* plan, const uint8_t* img1, const uint8_t* img2, int w, int h, int pitch,
@@ -603,7 +625,6 @@ int tma_search_plan(TmaSearchPlan* plan, const uint8_t* img1, const uint8_t* img
     if (err) snprintf(err, errlen, "cuTensorMapEncodeTiled failed (w=%d h=%d pitch=%d box=%dx%d)", w, h, pitch, g.box_w, g.box_h);
     return -1;
   }
-  plan->supported = 1;
   plan->bs = bs;
   plan->R = R;
   plan->seg = g.seg;
@@ -614,14 +635,21 @@ int tma_search_plan(TmaSearchPlan* plan, const uint8_t* img1, const uint8_t* img
   plan->threads = kThreads;
   plan->stages = kStages;
   plan->smem_bytes = g.smem;
+  // the kernel for this geometry must exist NOW: a geometry without an instantiation runs the generic kernel
+  const int have = dispatch(*plan, g.k64, g.a.pww, nullptr, 0, nullptr);
+  if (have < 0) {
+    if (err) snprintf(err, errlen, "cudaFuncSetAttribute(max dynamic shared memory) failed for the search kernel");
+    return -1;
+  }
+  plan->supported = have;
   return 0;
 }
 
-void launch_search_tma(const TmaSearchPlan& plan, ImgView i1, ImgView i2, MvView mv, int n,
-                       unsigned long long* counters, int sm_count, cudaStream_t s) {
+int launch_search_tma(const TmaSearchPlan& plan, ImgView i1, ImgView i2, MvView mv, int n,
+                      unsigned long long* counters, int sm_count, cudaStream_t s) {
   (void)i2;
   TmaGeom g;
-  make_geom(i1.w, i1.h, plan.bs, plan.R, &g);
+  if (!plan.supported || !make_geom(i1.w, i1.h, plan.bs, plan.R, &g)) return -1;
   TmaSearchArgs a = g.a;
   a.n_pairs = n;
   a.mv = mv.p;
@@ -630,19 +658,7 @@ void launch_search_tma(const TmaSearchPlan& plan, ImgView i1, ImgView i2, MvView
   const int total = a.gw * a.gh * n;
   int grid = sm_count * kMinCtas;
   if (grid > total) grid = total;
-#define BBME_CASE(BS_, SEG_, PWW_) \
-  if (!g.k64 && plan.bs == BS_ && plan.seg == SEG_ && a.pww == PWW_) { launch_inst<BS_, SEG_, PWW_, false>(plan, a, grid, s); return; }
-#define BBME_CASE64(BS_, SEG_, PWW_) \
-  if (g.k64 && plan.bs == BS_ && plan.seg == SEG_ && a.pww == PWW_) { launch_inst<BS_, SEG_, PWW_, true>(plan, a, grid, s); return; }
-#define BBME_CASES(BS_, SEG_) \
-  BBME_CASE(BS_, SEG_, 16) BBME_CASE(BS_, SEG_, 24) BBME_CASE(BS_, SEG_, 32) BBME_CASE(BS_, SEG_, 40) \
-  BBME_CASE(BS_, SEG_, 48) BBME_CASE(BS_, SEG_, 64)
-  BBME_CASES(8, 13) BBME_CASES(8, 11) BBME_CASES(8, 26) BBME_CASES(8, 43) BBME_CASES(16, 13) BBME_CASES(16, 11) BBME_CASES(32, 13) BBME_CASES(32, 11)
-  BBME_CASE64(16, 13, 40) BBME_CASE64(16, 13, 64) BBME_CASE64(16, 11, 40) BBME_CASE64(16, 11, 64)
-  BBME_CASE64(32, 13, 40) BBME_CASE64(32, 13, 64) BBME_CASE64(32, 11, 40) BBME_CASE64(32, 11, 64)
-#undef BBME_CASE64
-#undef BBME_CASES
-#undef BBME_CASE
+  return dispatch(plan, g.k64, a.pww, &a, grid, s) == 1 ? 0 : -1;
 }
 
 }  // namespace bbme

@@ -190,6 +190,32 @@ typedef struct {
 } bbme_host_link;
 int bbme_measure_host_link(bbme_ctx* ctx, size_t bytes, bbme_host_link* out);
 
+/* ---- the reference's calling pattern: one MF object per frame pair (main_class.cpp:45-50) ----
+ * bbme_mf_open returns a context planned for (device, geometry, sweeps) with chunk_pairs = slots = 1 -- a parked one of the
+ * same key if there is one, else a new one; bbme_mf_close parks it again (at most four idle contexts are kept, the oldest
+ * is destroyed beyond that).  MF::MF / MF::~MF of include/bbme/dropin.hpp are these two calls, so constructing an MF per
+ * pair does not pay context creation, device allocation and descriptor encoding every time.  On a planning error the
+ * context is still returned for bbme_last_error; pass it to bbme_mf_close.  Thread-safe. */
+int bbme_mf_open(bbme_ctx** ctx, int device, int width, int height, int num_levels, const int* search_size,
+                 const int* block_size, int sweeps, bbme_shape* out);
+void bbme_mf_close(bbme_ctx* ctx);
+void bbme_mf_cache_clear(void);
+
+/* ---- all GPUs of the box behind one call ----
+ * A pool owns one context per device (n_devices = 0: every visible device; devices = NULL: 0..n-1).  bbme_pool_plan plans
+ * them all alike; bbme_pool_estimate_batch cuts the n pairs into contiguous balanced shards, one host thread per device
+ * runs its shard through bbme_estimate_batch, and every field lands in the caller's flow[i] -- pairs are independent
+ * (one MF per pair), so there is no inter-GPU traffic and no collective. */
+typedef struct bbme_pool bbme_pool;
+int bbme_pool_create(bbme_pool** pool, int n_devices, const int* devices);
+void bbme_pool_destroy(bbme_pool* pool);
+int bbme_pool_device_count(const bbme_pool* pool);
+const char* bbme_pool_last_error(const bbme_pool* pool);
+int bbme_pool_plan(bbme_pool* pool, int width, int height, int num_levels, const int* search_size, const int* block_size,
+                   const bbme_options* opt, bbme_shape* out);
+int bbme_pool_estimate_batch(bbme_pool* pool, int n, const uint8_t* const* im1, const uint8_t* const* im2,
+                             size_t pitch_bytes, float* const* flow);
+
 /* Pinned host memory for asynchronous copies. */
 int bbme_host_alloc(void** p, size_t bytes);
 void bbme_host_free(void* p);

@@ -7,7 +7,12 @@
 //
 // Header-only: an application that used the reference's classes includes "motion_framework.h" / "rw_flow.h" from this
 // include/ directory instead of the reference's, links libbbme.so, and keeps its source unchanged.  What differs:
-//   * the work happens on a B200 (pad + pyramid in the constructor, everything else in calcMotionBlockMatching);
+//   * the work happens on a B200.  The constructor copies the two frames (the reference's constructor copies them too,
+//     with copyMakeBorder, motion_framework.cpp:60-61, so a caller may reuse or release its Mats afterwards) and takes a
+//     planned context for this geometry from the library's cache (bbme_mf_open); calcMotionBlockMatching() uploads the
+//     frames and runs pad, pyramid, search and regularisation; the destructor parks the context for the next MF of the
+//     same geometry (main builds one MF per pair, main_class.cpp:45);
+//   * the GPU is device 0 unless the BBME_DEVICE environment variable or MF::set_device() names another one;
 //   * errors: where the reference prints and calls getchar()/exit(1) (motion_framework.cpp:21-26, rw_flow.cpp), these
 //     classes print the same message to std::cout and call exit(1) (no getchar); define BBME_DROPIN_THROW to get a
 //     std::runtime_error instead;
@@ -65,15 +70,12 @@ class MF {
     if (num_levels <= 0) bbme_dropin::fatal("MF: num_levels must be > 0");                       // assert, motion_framework.cpp:7
     if (image1.rows != image2.rows || image1.cols != image2.cols) bbme_dropin::fatal("MF: image sizes differ");  // :8
     if (image1.type() != CV_8UC1 || image2.type() != CV_8UC1) bbme_dropin::fatal("MF: images must be CV_8UC1");
-    if (image1.step != image2.step) image2_ = image2.clone(), image1_ = image1.clone();
-    if (bbme_create(&ctx_, 0) != BBME_OK) bbme_dropin::fatal(std::string("MF: ") + bbme_last_error(nullptr));
-    bbme_options opt;
-    bbme_default_options(&opt);
-    opt.sweeps = sweeps;
+    image1_ = image1.clone();  // dense copies: the caller's Mats may change or go away before the estimation runs
+    image2_ = image2.clone();
     bbme_shape shape;
-    const int rc = bbme_plan(ctx_, image1.cols, image1.rows, num_levels, search_size, block_size, &opt, &shape);
+    const int rc = bbme_mf_open(&ctx_, device(), image1.cols, image1.rows, num_levels, search_size, block_size, sweeps, &shape);
     if (rc == BBME_E_NOPAD) fail("Could not find any multiples of the block size that match padded image dimensions");
-    if (rc != BBME_OK) fail(std::string("MF: ") + bbme_last_error(ctx_));
+    if (rc != BBME_OK) fail(std::string("MF: ") + (ctx_ ? bbme_last_error(ctx_) : bbme_last_error(nullptr)));
     padded_height = shape.padded_height;
     padded_width = shape.padded_width;
     padding_x = shape.padding_x;
@@ -97,7 +99,18 @@ class MF {
   }
 
   ~MF() {
-    if (ctx_) bbme_destroy(ctx_);
+    if (ctx_) bbme_mf_close(ctx_);
+  }
+
+  // Which GPU MF objects constructed from now on use (default: BBME_DEVICE or 0).
+  static void set_device(int d) { device_ref() = d; }
+  static int device() {
+    int d = device_ref();
+    if (d < 0) {
+      const char* e = std::getenv("BBME_DEVICE");
+      d = e ? std::atoi(e) : 0;
+    }
+    return d;
   }
 
   int padded_height;
@@ -110,10 +123,15 @@ class MF {
  private:
   MF(const MF&);
   MF& operator=(const MF&);
+  static int& device_ref() {
+    static int d = -1;
+    return d;
+  }
   void fail(const std::string& msg) {
-    if (ctx_) bbme_destroy(ctx_);
+    const std::string m = msg;  // the text may live in the context
+    if (ctx_) bbme_mf_close(ctx_);
     ctx_ = nullptr;
-    bbme_dropin::fatal(msg);
+    bbme_dropin::fatal(m);
   }
   bbme_ctx* ctx_;
   cv::Mat image1_, image2_;

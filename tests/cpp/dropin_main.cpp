@@ -2,8 +2,10 @@
 // against include/ + libbbme.so.  Reads two raw 8-bit frames, runs MF, strips the padding like main() does and writes
 // the field with Flow::WriteFlowFile.  tests/test_gpu_dropin_cpp.py builds it, runs it and compares with the oracle.
 //   usage: dropin_main <w> <h> <frame1.raw> <frame2.raw> <out.flo> <levels> <search_size...> <block_size...>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "motion_framework.h"
@@ -47,5 +49,24 @@ int main(int argc, char** argv) {
   file.ReadFlowFile(back, argv[5]);
   double err = file.CalculateMSE(back, mvs);
   printf("padded %dx%d pad (%d,%d) self-AEE %.6f\n", motion_pair.padded_width, motion_pair.padded_height, pad_x, pad_y, err);
-  return err == 0.0 ? 0 : 4;
+  if (err != 0.0) return 4;
+
+  // The reference's caller builds one MF per frame pair (main_class.cpp:45-50) and its constructor COPIES the frames
+  // (copyMakeBorder, motion_framework.cpp:60-61): a video loop may overwrite its buffers right after construction.
+  double ms = 0.0;
+  const int reps = 5;
+  for (int r = 0; r < reps; ++r) {
+    cv::Mat a = image1.clone(), b = image2.clone();
+    const auto t0 = std::chrono::steady_clock::now();
+    {
+      MF again(a, b, search_size.data(), block_size.data(), num_levels);
+      memset(a.data, 0, (size_t)w * h);  // the caller reuses its buffers
+      memset(b.data, 255, (size_t)w * h);
+      cv::Mat f2 = again.calcMotionBlockMatching();
+      if (memcmp(f2.data, flow_res.data, (size_t)flow_res.rows * flow_res.cols * 8) != 0) return 6;
+    }
+    ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  }
+  printf("mf_ms_per_pair %.3f (constructor + calcMotionBlockMatching + destructor, %d objects)\n", ms / reps, reps);
+  return 0;
 }

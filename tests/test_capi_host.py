@@ -228,3 +228,18 @@ def test_expand_compact_matches_numpy():
         want = np.repeat(np.repeat(mv, 2, axis=0), 2, axis=1).astype(np.float32)
         assert np.array_equal(out, want)
         assert np.isnan(buf[:align]).all() and np.isnan(buf[align + out.size:]).all()
+
+
+def test_pool_and_mf_cache_fail_loudly_without_a_gpu():
+    """No device, no fallback: the multi-GPU pool and the MF context cache report the CUDA error."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = _lib.load()
+    p = C.c_void_p()
+    assert lib.bbme_pool_create(C.byref(p), 0, None) == -6 and not p.value
+    assert b"no CPU fallback" in lib.bbme_last_error(None)
+    ctx = C.c_void_p()
+    rc = lib.bbme_mf_open(C.byref(ctx), 0, 64, 64, 1, (C.c_int * 1)(16), (C.c_int * 1)(8), 2, None)
+    assert rc == -6 and not ctx.value
+    lib.bbme_mf_cache_clear()

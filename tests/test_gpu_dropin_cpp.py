@@ -27,6 +27,7 @@ def test_cpp_dropin_matches_oracle(tmp_path, oracle):
     res = subprocess.run(args, capture_output=True, text=True)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "padded 128x96 pad (3,3)" in res.stdout
+    assert "mf_ms_per_pair" in res.stdout  # five more MF objects on reused buffers gave the same field
     got = bb.Flow().ReadFlowFile(out)
     want, _ = oracle.estimate(f1, f2, ss, bs, 2)
     assert np.array_equal(got, want[3:3 + h, 3:3 + w])
