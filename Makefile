@@ -7,7 +7,7 @@ NVFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xco
 LIB := $(PKG)/libbbme.so
 OBJS := $(CSRC)/kernels.o $(CSRC)/search_tma.o $(CSRC)/capi.o $(CSRC)/flo.o $(CSRC)/hostpool.o $(CSRC)/multi.o
 
-all: $(LIB) oracle
+all: $(LIB) oracle tools/color_flow
 
 $(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/kernels.h $(CSRC)/hostpool.h include/bbme.h
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@
@@ -23,6 +23,10 @@ $(CSRC)/multi.o: $(CSRC)/multi.cpp include/bbme.h
 
 $(LIB): $(OBJS)
 	$(NVCC) -gencode arch=compute_100a,code=sm_100a -shared -o $@ $(OBJS) -cudart static -lpthread
+
+# color_flow-compatible command-line tool (middlebury/flow-code/color_flow.cpp:68-98); host-only
+tools/color_flow: tools/color_flow.cpp include/bbme.h $(LIB)
+	g++ -O2 -std=c++17 -Wall -Iinclude -o $@ tools/color_flow.cpp -L$(PKG) -lbbme -Wl,-rpath,'$$ORIGIN/../$(PKG)'
 
 oracle:
 	$(MAKE) -C oracle

@@ -37,7 +37,7 @@ class BbmeStats(C.Structure):
 class BbmeOptions(C.Structure):
     _fields_ = [
         ("sweeps", C.c_int), ("chunk_pairs", C.c_int), ("slots", C.c_int),
-        ("search_kernel", C.c_int), ("collect_stats", C.c_int), ("keep_search_mv", C.c_int),
+        ("search_kernel", C.c_int), ("collect_stats", C.c_int), ("keep_search_mv", C.c_int), ("search_variant", C.c_int),
     ]
 
 
@@ -94,6 +94,8 @@ SIGNATURES = {
     "bbme_stage_pyrdown": (_I, [_P, _P, _I, _I, _P]),
     "bbme_stage_resize": (_I, [_P, _P, _I, _I, _I, _P]),
     "bbme_stage_search": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _I, C.POINTER(BbmeStats)]),
+    "bbme_stage_search_raster": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "bbme_stage_compensate": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "bbme_stage_regularize": (_I, [_P, _P, _P, _I, _I, _I, C.c_float, _I, _P, C.POINTER(C.c_uint32)]),
     "bbme_stage_divide": (_I, [_P, _P, _I, _I, _P]),
     "bbme_stage_copy_mvs": (_I, [_P, _P, _I, _I, _I, _I, _P]),

@@ -82,7 +82,7 @@ class Estimator:
     """A planned context: one GPU, fixed geometry, batched estimation (bbme_plan / bbme_estimate*)."""
 
     def __init__(self, width, height, search_size, block_size, num_levels=None, sweeps=2, device=0, chunk_pairs=1,
-                 slots=1, search_kernel=0, collect_stats=False, keep_search_mv=False):
+                 slots=1, search_kernel=0, collect_stats=False, keep_search_mv=False, search_variant=0):
         self._lib = _lib.load()
         self._ctx = C.c_void_p()
         rc = self._lib.bbme_create(C.byref(self._ctx), int(device))
@@ -98,6 +98,7 @@ class Estimator:
         opt.search_kernel = int(search_kernel)
         opt.collect_stats = int(bool(collect_stats))
         opt.keep_search_mv = int(bool(keep_search_mv))
+        opt.search_variant = int(search_variant)
         sh = BbmeShape()
         try:
             _check(self._lib, self._ctx,
@@ -308,6 +309,28 @@ class Estimator:
                                            mv.ctypes.data, kernel, C.byref(st)), "stage_search")
         return mv, {k: getattr(st, k) for k, _ in BbmeStats._fields_}
 
+    def stage_search_raster(self, im1, im2, block_size, search_size, pred=None):
+        """MF::calcLevelBM with MF::find_min_block (motion_framework.cpp:246-294) instead of the spiral search."""
+        im1 = np.ascontiguousarray(im1, np.uint8)
+        im2 = np.ascontiguousarray(im2, np.uint8)
+        h, w = im1.shape
+        mv = np.zeros((h // block_size, w // block_size, 2), np.int16) if pred is None else np.ascontiguousarray(pred, np.int16).copy()
+        _check(self._lib, self._ctx,
+               self._lib.bbme_stage_search_raster(self._ctx, im1.ctypes.data, im2.ctypes.data, w, h, block_size, search_size,
+                                                  mv.ctypes.data), "stage_search_raster")
+        return mv
+
+    def stage_compensate(self, im2, block_size, mv):
+        """MF::draw_MVimage (motion_framework.cpp:887-905): the motion-compensated frame from image 2 and a block-granular field."""
+        im2 = np.ascontiguousarray(im2, np.uint8)
+        h, w = im2.shape
+        mv = np.ascontiguousarray(mv, np.int16)
+        out = np.empty((h, w), np.uint8)
+        _check(self._lib, self._ctx,
+               self._lib.bbme_stage_compensate(self._ctx, im2.ctypes.data, w, h, block_size, mv.ctypes.data, out.ctypes.data),
+               "stage_compensate")
+        return out
+
     def stage_regularize(self, im1, im2, block_size, lam, mult, mv):
         im1 = np.ascontiguousarray(im1, np.uint8)
         im2 = np.ascontiguousarray(im2, np.uint8)
@@ -433,6 +456,11 @@ class MF:
 
     def calcMotionBlockMatching(self):
         return self._est.estimate(self._im1, self._im2)
+
+    def draw_MVimage(self):
+        """Mirror of MF::draw_MVimage (motion_framework.cpp:887-905) as the commented call site :213-216 would use it after
+        calcMotionBlockMatching(): block size 2, level 0 -- the motion-compensated padded frame."""
+        return self._est.stage_compensate(self._est.level_image(0, 1), 2, self._est.level_mv(0, which=0))
 
     def stats(self):
         return self._est.stats()

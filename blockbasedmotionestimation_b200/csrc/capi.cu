@@ -282,13 +282,13 @@ int run_chunk(bbme_ctx* c, Slot& s, int n, const uint8_t* d_in1, const uint8_t* 
     }
     mark(c, s, TAG_OTHER);
     const TmaSearchPlan& tplan = seq ? s.tma_seq[l] : s.tma[l];
-    const bool use_tma = tplan.supported && c->opt.search_kernel != 1;
+    const bool use_tma = tplan.supported && c->opt.search_kernel != 1 && c->opt.search_variant == 0;
     unsigned long long* ctrs = c->opt.collect_stats ? s.counters : nullptr;
     if (use_tma) {
       if (launch_search_tma(tplan, i1, i2, field, n, ctrs, c->sm_count, st) != 0)
         return fail(c, BBME_E_CUDA, "level %d: no TMA search kernel for block %d, R %d (plan and launch disagree)", l, g, R);
     } else {
-      launch_search_generic(i1, i2, field, g, R, n, ctrs, st);
+      launch_search_generic(i1, i2, field, g, R, n, ctrs, st, c->opt.search_variant);
     }
     ++c->launches;
     ++c->search_launches;
@@ -311,7 +311,7 @@ int run_chunk(bbme_ctx* c, Slot& s, int n, const uint8_t* d_in1, const uint8_t* 
       ra.list0 = s.list0; ra.list1 = s.list1; ra.nv = s.nv; ra.stamp = s.stamp;
       ra.wl_plane = c->cap[0];
       ra.ctr = s.ctr;
-      ra.hist = nullptr;
+      ra.hist = s.hist ? s.hist + 64 * l : nullptr;  // BBME_REG_PROFILE: 8 words per block size, 64 per level
       if (launch_reg_level(ra, c->opt.sweeps, lambda, 1, 0, n, c->sm_count, st) != 0)
         return fail(c, BBME_E_CUDA, "regularisation kernel launch failed at level %d: %s", l, cudaGetErrorString(cudaGetLastError()));
       ++c->launches;
@@ -452,6 +452,16 @@ int collect_after_sync(bbme_ctx* c) {
     std::vector<uint32_t> hh((size_t)kHistSweeps * 64);
     CUDA_TRY(c, cudaMemcpy(hh.data(), s.hist, hh.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     CUDA_TRY(c, cudaMemset(s.hist, 0, hh.size() * sizeof(uint32_t)));
+    if (getenv("BBME_REG_PROFILE")) {
+      for (int l = 0; l < c->shape.num_levels; ++l)
+        for (int k = 1; k < 8; ++k) {
+          const uint32_t* q = &hh[(size_t)l * 64 + 8 * k];
+          if (!q[0] && !q[1]) continue;
+          fprintf(stderr, "regprofile level %d bs %d: classify %.1f us, first pass %.1f us (%u listed, %u deferred), %u later rounds %.1f us (%u blocks)\n",
+                  l, 1 << k, q[0] * 1e-3, q[1] * 1e-3, q[4], q[6], q[3], q[2] * 1e-3, q[5]);
+        }
+      continue;
+    }
     for (int sw = 0; sw < kHistSweeps; ++sw) {
       const uint32_t* q = &hh[(size_t)sw * 64];
       if (!q[0] && !q[63]) continue;
@@ -558,6 +568,7 @@ void bbme_default_options(bbme_options* o) {
   o->search_kernel = 0;
   o->collect_stats = 0;
   o->keep_search_mv = 0;
+  o->search_variant = 0;
 }
 
 int bbme_version(void) { return BBME_VERSION; }
@@ -633,9 +644,14 @@ int bbme_plan(bbme_ctx* c, int width, int height, int num_levels, const int* sea
   bbme_options o;
   bbme_default_options(&o);
   if (opt) o = *opt;
-  if (o.sweeps < 0 || o.chunk_pairs < 1 || o.slots < 1 || o.slots > 4 || o.search_kernel < 0 || o.search_kernel > 2)
-    return fail(c, BBME_E_ARG, "bbme_plan: bad options (sweeps=%d chunk_pairs=%d slots=%d search_kernel=%d)", o.sweeps,
-                o.chunk_pairs, o.slots, o.search_kernel);
+  if (o.sweeps < 0 || o.chunk_pairs < 1 || o.slots < 1 || o.slots > 4 || o.search_kernel < 0 || o.search_kernel > 2 ||
+      o.search_variant < 0 || o.search_variant > 1 || (o.search_variant == 1 && o.search_kernel == 2))
+    return fail(c, BBME_E_ARG, "bbme_plan: bad options (sweeps=%d chunk_pairs=%d slots=%d search_kernel=%d search_variant=%d)",
+                o.sweeps, o.chunk_pairs, o.slots, o.search_kernel, o.search_variant);
+  if (o.search_variant == 1)
+    for (int l = 0; l < sh.num_levels; ++l)
+      if (2 * radius_of(sh.search_size[l], sh.block_size[l]) + 1 > 362)
+        return fail(c, BBME_E_ARG, "bbme_plan: search_variant 1 supports +-R up to 180 (level %d)", l);
   c->shape = sh;
   c->opt = o;
   const int L = sh.num_levels;
@@ -668,7 +684,7 @@ int bbme_plan(bbme_ctx* c, int width, int height, int num_levels, const int* sea
         (rc = dev_alloc(c, &s.ctr, n * kCtrWords, true)) || (rc = dev_alloc(c, &s.counters, (size_t)2, true)) ||
         (rc = dev_alloc(c, &s.out, n * (c->out_plane / 4 + 64), false)))
       return rc;
-    if (getenv("BBME_FIX_HIST") && (rc = dev_alloc(c, &s.hist, (size_t)kHistSweeps * 64, true))) return rc;
+    if ((getenv("BBME_FIX_HIST") || getenv("BBME_REG_PROFILE")) && (rc = dev_alloc(c, &s.hist, (size_t)kHistSweeps * 64, true))) return rc;
     for (int l = 0; l < L; ++l) {
       memset(&s.tma[l], 0, sizeof(s.tma[l]));
       memset(&s.tma_seq[l], 0, sizeof(s.tma_seq[l]));
@@ -821,12 +837,20 @@ static int estimate_batch_async_impl(bbme_ctx* c, int n, int factor, const uint8
   for (int start = 0; start < n; start += chunk, ++ci) {
     Slot& s = c->slots[ci % c->slots.size()];
     const int m = (n - start < chunk) ? (n - start) : chunk;
-    for (int i = 0; i < m; ++i) {
-      CUDA_TRY(c, cudaMemcpy2DAsync(s.in1 + (size_t)i * in_plane, in_pitch, im1[start + i], pitch, w, h,
-                                    cudaMemcpyHostToDevice, s.stream));
-      CUDA_TRY(c, cudaMemcpy2DAsync(s.in2 + (size_t)i * in_plane, in_pitch, im2[start + i], pitch, w, h,
-                                    cudaMemcpyHostToDevice, s.stream));
-    }
+    // frames that follow each other in host memory (an array of frames: plane i + 1 starts where plane i ends) go up as
+    // one copy per image instead of one per pair
+    auto upload = [&](uint8_t* dst, const uint8_t* const* src) -> cudaError_t {
+      bool contiguous = in_plane == in_pitch * (size_t)h;
+      for (int i = 1; i < m && contiguous; ++i) contiguous = src[i] == src[i - 1] + pitch * (size_t)h;
+      if (contiguous) return cudaMemcpy2DAsync(dst, in_pitch, src[0], pitch, w, (size_t)h * m, cudaMemcpyHostToDevice, s.stream);
+      for (int i = 0; i < m; ++i) {
+        cudaError_t e = cudaMemcpy2DAsync(dst + (size_t)i * in_plane, in_pitch, src[i], pitch, w, h, cudaMemcpyHostToDevice, s.stream);
+        if (e != cudaSuccess) return e;
+      }
+      return cudaSuccess;
+    };
+    CUDA_TRY(c, upload(s.in1, im1 + start));
+    CUDA_TRY(c, upload(s.in2, im2 + start));
     if (factor > 1) {
       int rc = run_chunk_graphed(c, s, m, s.in1, s.in2, in_pitch, in_plane, s.out, out_plane, nullptr, 0, factor);
       if (rc) return rc;
@@ -1163,6 +1187,46 @@ int bbme_stage_search(bbme_ctx* c, const uint8_t* im1, const uint8_t* im2, int w
     st->search_kernel_used = plan.supported ? 2u : 1u;
     st->search_launches = 1;
   }
+  return BBME_OK;
+}
+
+int bbme_stage_search_raster(bbme_ctx* c, const uint8_t* im1, const uint8_t* im2, int w, int h, int bs, int ss, int16_t* mv) {
+  if (!c || !im1 || !im2 || !mv || !is_pow2(bs) || bs < 2 || w % bs || h % bs) return BBME_E_ARG;
+  const int R = radius_of(ss, bs);
+  if (2 * R + 1 > 362) return fail(c, BBME_E_ARG, "stage_search_raster: +-R up to 180");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  Scratch sc;
+  int pitch = 0, rc;
+  uint8_t *d1 = nullptr, *d2 = nullptr;
+  if ((rc = upload_image(c, sc, im1, w, h, &pitch, &d1)) || (rc = upload_image(c, sc, im2, w, h, &pitch, &d2))) return rc;
+  const int gw = w / bs, gh = h / bs;
+  short2* dmv = sc.get<short2>((size_t)gw * gh, false);
+  if (!dmv) return fail(c, BBME_E_NOMEM, "stage: cudaMalloc failed");
+  CUDA_TRY(c, cudaMemcpy(dmv, mv, (size_t)gw * gh * sizeof(short2), cudaMemcpyHostToDevice));
+  ImgView i1{d1, w, h, pitch, (size_t)pitch * h}, i2{d2, w, h, pitch, (size_t)pitch * h};
+  MvView f{dmv, gw, gh, (size_t)gw * gh};
+  launch_search_generic(i1, i2, f, bs, R, 1, nullptr, 0, 1);
+  CUDA_TRY(c, cudaDeviceSynchronize());
+  CUDA_TRY(c, cudaMemcpy(mv, dmv, (size_t)gw * gh * sizeof(short2), cudaMemcpyDeviceToHost));
+  return BBME_OK;
+}
+
+int bbme_stage_compensate(bbme_ctx* c, const uint8_t* im2, int w, int h, int bs, const int16_t* mv, uint8_t* out) {
+  if (!c || !im2 || !mv || !out || !is_pow2(bs) || bs < 2 || w % bs || h % bs) return BBME_E_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  Scratch sc;
+  int pitch = 0, rc;
+  uint8_t* d2 = nullptr;
+  if ((rc = upload_image(c, sc, im2, w, h, &pitch, &d2))) return rc;
+  const int gw = w / bs, gh = h / bs;
+  short2* dmv = sc.get<short2>((size_t)gw * gh, false);
+  uint8_t* dout = sc.get<uint8_t>((size_t)pitch * h, true);
+  if (!dmv || !dout) return fail(c, BBME_E_NOMEM, "stage: cudaMalloc failed");
+  CUDA_TRY(c, cudaMemcpy(dmv, mv, (size_t)gw * gh * sizeof(short2), cudaMemcpyHostToDevice));
+  ImgView i2{d2, w, h, pitch, (size_t)pitch * h};
+  launch_compensate(i2, dmv, gw, (size_t)gw * gh, bs, dout, pitch, (size_t)pitch * h, 1, 0);
+  CUDA_TRY(c, cudaDeviceSynchronize());
+  CUDA_TRY(c, cudaMemcpy2D(out, w, dout, pitch, w, h, cudaMemcpyDeviceToHost));
   return BBME_OK;
 }
 

@@ -285,8 +285,12 @@ void launch_pyrdown(ImgView src1, ImgView src2, uint8_t* dst1, uint8_t* dst2, in
 // MF::calcLevelBM + find_min_block_spiral (motion_framework.cpp:226-244, 296-422) for any power-of-two block
 // size: one CTA per block, threads stride over the (2R+1)^2 displacements, argmin on the key (SAD, spiral rank).
 // Bring-up / fallback path (block sizes the TMA kernel does not cover) and the in-library cross-check of it.
+// variant 1 = MF::find_min_block (motion_framework.cpp:246-294, the raster-scan search the commented line :235 would call): no
+// centre test -- the window is clamped to the image (:260,262) and an empty window keeps the prediction (:251-252) -- and ties
+// go to the smaller L1 distance from the block's position in image 1, then to the earlier position in row-major order
+// (:271-283): key = SAD << 32 | L1 << 17 | row-major index (needs 2R + 1 <= 362, L1 < 2^15).
 __global__ void __launch_bounds__(128) k_search_generic(ImgView i1, ImgView i2, MvView mv, int bs, int R,
-                                                        unsigned long long* __restrict__ counters) {
+                                                        unsigned long long* __restrict__ counters, int variant) {
   const int pair = blockIdx.y;
   const int bx = blockIdx.x % mv.gw, by = blockIdx.x / mv.gw;
   const int x = bx * bs, y = by * bs;
@@ -294,7 +298,7 @@ __global__ void __launch_bounds__(128) k_search_generic(ImgView i1, ImgView i2, 
   short2* slot = mv.p + (size_t)pair * mv.plane + (size_t)by * mv.gw + bx;
   const short2 pred = *slot;
   const int x2 = x + pred.x, y2 = y + pred.y;
-  if (x2 < 0 || y2 < 0 || x2 + bs > w || y2 + bs > h) {  // :304-310 -> MV 0, no search
+  if (variant == 0 && (x2 < 0 || y2 < 0 || x2 + bs > w || y2 + bs > h)) {  // :304-310 -> MV 0, no search
     if (threadIdx.x == 0) *slot = make_short2(0, 0);
     return;
   }
@@ -307,7 +311,8 @@ __global__ void __launch_bounds__(128) k_search_generic(ImgView i1, ImgView i2, 
     const int px = x2 + dx, py = y2 + dy;
     if (px < 0 || py < 0 || px + bs > w || py + bs > h) continue;  // skipped, walk continues (:335-336)
     const uint32_t sad = sad_block_unaligned(a, b0 + (size_t)py * pitch + px, pitch, bs);
-    const unsigned long long key = ((unsigned long long)sad << 32) | spiral_rank(dx, dy);
+    const uint32_t rank = variant == 0 ? spiral_rank(dx, dy) : (((uint32_t)(abs(pred.x + dx) + abs(pred.y + dy)) << 17) | (uint32_t)c);
+    const unsigned long long key = ((unsigned long long)sad << 32) | rank;
     best = key < best ? key : best;
   }
 #pragma unroll
@@ -323,7 +328,13 @@ __global__ void __launch_bounds__(128) k_search_generic(ImgView i1, ImgView i2, 
     // decode the rank back into (dx, dy) by evaluating the same closed form over the ring
     const uint32_t rank = (uint32_t)best;
     int dx = 0, dy = 0;
-    if (rank != 0) {
+    if (variant != 0) {
+      if (best != ~0ull) {  // else: empty window, the prediction stays
+        const int c = (int)(rank & 0x1ffffu);
+        dx = c % n - R;
+        dy = c / n - R;
+      }
+    } else if (rank != 0) {
       int r = 1;
       while ((uint32_t)((2 * r + 1) * (2 * r + 1)) <= rank) ++r;
       const int base = (2 * r - 1) * (2 * r - 1);
@@ -335,8 +346,8 @@ __global__ void __launch_bounds__(128) k_search_generic(ImgView i1, ImgView i2, 
     }
     *slot = make_short2((short)(pred.x + dx), (short)(pred.y + dy));
     if (counters) {
-      const int nx = min(R, w - bs - x2) - max(-R, -x2) + 1;
-      const int ny = min(R, h - bs - y2) - max(-R, -y2) + 1;
+      const int nx = max(min(R, w - bs - x2) - max(-R, -x2) + 1, 0);
+      const int ny = max(min(R, h - bs - y2) - max(-R, -y2) + 1, 0);
       atomicAdd(&counters[0], (unsigned long long)(nx * ny));
       atomicAdd(&counters[1], (unsigned long long)(nx * ny) * (unsigned long long)(bs * bs));
     }
@@ -344,9 +355,33 @@ __global__ void __launch_bounds__(128) k_search_generic(ImgView i1, ImgView i2, 
 }
 
 void launch_search_generic(ImgView i1, ImgView i2, MvView mv, int bs, int R, int n, unsigned long long* counters,
-                           cudaStream_t s) {
+                           cudaStream_t s, int variant) {
   dim3 grid(mv.gw * mv.gh, n);
-  k_search_generic<<<grid, 128, 0, s>>>(i1, i2, mv, bs, R, counters);
+  k_search_generic<<<grid, 128, 0, s>>>(i1, i2, mv, bs, R, counters, variant);
+}
+
+// MF::draw_MVimage (motion_framework.cpp:887-905): the motion-compensated frame.  One thread per 4 output bytes of a block row
+// (2x2 blocks: per block row); blocks whose source leaves the image keep the bytes already in `out`.
+__global__ void __launch_bounds__(256) k_compensate(ImgView i2, const short2* __restrict__ mv, int gw, size_t mv_plane, int bs,
+                                                    uint8_t* __restrict__ out, int out_pitch, size_t out_plane) {
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 2;  // two pixels per thread (block sizes are even)
+  const int y = blockIdx.y;
+  const int pair = blockIdx.z;
+  if (x >= i2.w || y >= i2.h) return;
+  const int bx = x / bs, by = y / bs;
+  const short2 m = __ldg(&mv[(size_t)pair * mv_plane + (size_t)by * gw + bx]);
+  const int x2 = bx * bs + m.x, y2 = by * bs + m.y;
+  if (x2 < 0 || x2 > i2.w - bs || y2 < 0 || y2 > i2.h - bs) return;  // :897-898
+  const uint8_t* src = i2.p + (size_t)pair * i2.plane + (size_t)(y2 + (y - by * bs)) * i2.pitch + x2 + (x - bx * bs);
+  uint8_t* dst = out + (size_t)pair * out_plane + (size_t)y * out_pitch + x;
+  dst[0] = __ldg(src);
+  dst[1] = __ldg(src + 1);
+}
+
+void launch_compensate(ImgView i2, const short2* mv, int gw, size_t mv_plane, int bs, uint8_t* out, int out_pitch,
+                       size_t out_plane, int n, cudaStream_t s) {
+  dim3 grid((i2.w / 2 + 255) / 256, i2.h, n);
+  k_compensate<<<grid, 256, 0, s>>>(i2, mv, gw, mv_plane, bs, out, out_pitch, out_plane);
 }
 
 // ============================================================================================ MV plumbing
@@ -1225,24 +1260,41 @@ __device__ __forceinline__ uint32_t sad_small(const uint32_t* A, const uint8_t* 
 // and B: S_A = (#B) * d(A, B), S_B = (#A) * d(A, B) (integer-valued, exact in float like the reference's running sum),
 // B wins iff E_B < E_A (strict: index 0 wins ties, :653-659).  Returns false if there are more than two distinct vectors
 // (the caller defers the block to the nine-slot evaluator); *out = the block's new vector otherwise.
-template <int BS>
-__device__ __forceinline__ bool reg_eval_small_fast(const RegArgs& a, int pair, const short2* O, const short2* P, int bx, int by,
-                                                    uint32_t* out) {
+// The nine candidate vectors of block (bx, by), packed: A0 = the block's own (slot 0), pk[0..7] = slots 1..8
+// [L, R, DR, UL, UR, U, D, DL]; a missing neighbour holds A0 (it drops out of every count below).  Split from the evaluation so
+// that the caller can issue these loads one iteration ahead (the evaluation's only other memory round trip is the windows).
+__device__ __forceinline__ void small_gather(const RegArgs& a, const short2* O, const short2* P, int bx, int by, uint32_t& A0,
+                                             uint32_t (&pk)[8]) {
   const int gw = a.gw, gh = a.gh;
   const int idx = by * gw + bx;
   const bool up = by > 0, dn = by < gh - 1, lf = bx > 0, rt = bx < gw - 1;
   const uint32_t* Ou = reinterpret_cast<const uint32_t*>(O);
   const uint32_t* Pu = reinterpret_cast<const uint32_t*>(P);
-  const uint32_t A0 = Ou[idx];
-  uint32_t pk[8];  // slots 1..8: L, R, DR, UL, UR, U, D, DL; a missing neighbour holds A and drops out below
-  pk[0] = lf ? Pu[idx - 1] : A0;
-  pk[1] = rt ? Ou[idx + 1] : A0;
-  pk[2] = (dn && rt) ? Ou[idx + gw + 1] : A0;
-  pk[3] = (up && lf) ? Pu[idx - gw - 1] : A0;
-  pk[4] = (up && rt) ? Pu[idx - gw + 1] : A0;
-  pk[5] = up ? Pu[idx - gw] : A0;
-  pk[6] = dn ? Ou[idx + gw] : A0;
-  pk[7] = (dn && lf) ? Ou[idx + gw - 1] : A0;
+  A0 = Ou[idx];
+  pk[0] = Pu[lf ? idx - 1 : idx];
+  pk[1] = Ou[rt ? idx + 1 : idx];
+  pk[2] = Ou[(dn && rt) ? idx + gw + 1 : idx];
+  pk[3] = Pu[(up && lf) ? idx - gw - 1 : idx];
+  pk[4] = Pu[(up && rt) ? idx - gw + 1 : idx];
+  pk[5] = Pu[up ? idx - gw : idx];
+  pk[6] = Ou[dn ? idx + gw : idx];
+  pk[7] = Ou[(dn && lf) ? idx + gw - 1 : idx];
+}
+
+template <int BS>
+__device__ __forceinline__ bool reg_eval_small_fast(const RegArgs& a, int pair, int bx, int by, uint32_t A0, uint32_t (&pk)[8],
+                                                    uint32_t* out) {
+  const int gw = a.gw, gh = a.gh;
+  const bool up = by > 0, dn = by < gh - 1, lf = bx > 0, rt = bx < gw - 1;
+  // a missing neighbour was read from the block's own index (possibly from the NEW field): it counts as A
+  pk[0] = lf ? pk[0] : A0;
+  pk[1] = rt ? pk[1] : A0;
+  pk[2] = (dn && rt) ? pk[2] : A0;
+  pk[3] = (up && lf) ? pk[3] : A0;
+  pk[4] = (up && rt) ? pk[4] : A0;
+  pk[5] = up ? pk[5] : A0;
+  pk[6] = dn ? pk[6] : A0;
+  pk[7] = (dn && lf) ? pk[7] : A0;
   uint32_t B = A0;
 #pragma unroll
   for (int i = 7; i >= 0; --i) B = (pk[i] != A0) ? pk[i] : B;  // the lowest slot that differs
@@ -1335,24 +1387,30 @@ __device__ __forceinline__ uint32_t team_partial_sad(const uint8_t* blk, const u
 // the DISTINCT in-image vectors (a team-uniform list) are summed row-wise by all lanes, several per memory round trip
 // (16x16 and up: three windows, one row each; 8x8: four windows, each half of the team takes two); a shuffle argmin over
 // (energy, slot) gives every lane the winner.  ~300 instructions per lane instead of ~1600.
-template <int BSK>  // 8, 16, or 32 (= 32 and larger)
-__device__ __forceinline__ uint32_t reg_eval_team_lean(const RegArgs& a, int pair, const short2* O, const short2* P, int bx,
-                                                       int by, int tl, bool live) {
-  constexpr int TEAMSZ = BSK >= 32 ? 32 : 16;
-  constexpr uint32_t FULL = 0xffffffffu;
-  const int gw = a.gw, gh = a.gh, bs = a.bs;
-  const int lane = threadIdx.x & 31;
-  const int base = lane - tl;  // first lane of this team inside the warp
-  const int idx = by * gw + bx;
-  // slot -> neighbour: [C, L, R, DR, UL, UR, U, D, DL] (:441-449); L, UL, UR, U come from the new field
+// Slot tl of block (bx, by): [C, L, R, DR, UL, UR, U, D, DL] (:441-449); L, UL, UR, U come from the new field.  Returns the
+// slot's vector (an invalid slot returns the entry at the block's own index; the evaluator replaces it by C's).
+__device__ __forceinline__ uint32_t team_slot_load(const RegArgs& a, const short2* O, const short2* P, int bx, int by, int tl,
+                                                   bool& valid) {
+  const int gw = a.gw, gh = a.gh;
   const int s = tl < 9 ? tl : 0;
   const int ddx = (s == 2 || s == 3 || s == 5) ? 1 : ((s == 1 || s == 4 || s == 8) ? -1 : 0);
   const int ddy = (s == 3 || s == 7 || s == 8) ? 1 : ((s == 4 || s == 5 || s == 6) ? -1 : 0);
   const bool from_new = s == 1 || s == 4 || s == 5 || s == 6;
   const int nx = bx + ddx, ny = by + ddy;
-  const bool valid = tl < 9 && nx >= 0 && nx < gw && ny >= 0 && ny < gh;
+  valid = tl < 9 && nx >= 0 && nx < gw && ny >= 0 && ny < gh;
   const uint32_t* src = reinterpret_cast<const uint32_t*>(from_new ? P : O);
-  uint32_t my = src[valid ? idx + ddy * gw + ddx : idx];
+  const int idx = by * gw + bx;
+  return src[valid ? idx + ddy * gw + ddx : idx];
+}
+
+template <int BSK>  // 8, 16, or 32 (= 32 and larger)
+__device__ __forceinline__ uint32_t reg_eval_team_lean(const RegArgs& a, int pair, int bx, int by, int tl, bool live, uint32_t my,
+                                                       bool valid) {
+  constexpr int TEAMSZ = BSK >= 32 ? 32 : 16;
+  constexpr uint32_t FULL = 0xffffffffu;
+  const int bs = a.bs;
+  const int lane = threadIdx.x & 31;
+  const int base = lane - tl;  // first lane of this team inside the warp
   const uint32_t c0 = __shfl_sync(FULL, my, base);  // slot 0 is always valid and reads O
   if (!valid) my = c0;
   // first slot of the team that holds my vector (invalid slots hold C's, i.e. slot 0's)
@@ -1462,6 +1520,12 @@ __device__ __forceinline__ uint32_t reg_eval_team_lean(const RegArgs& a, int pai
 // reached whatever the interleaving), which shortens the tail because the list is in raster order.
 namespace cg = cooperative_groups;
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 struct LevelCtx {
   uint32_t* cnt;     // three rotating list counters + two alternating counters of the deferred list (shared memory of rank 0)
   int rank, cs;
@@ -1482,31 +1546,49 @@ __device__ __forceinline__ void level_classify(const RegArgs& a, int pair, const
   uint32_t* Y = reinterpret_cast<uint32_t*>(a.Y + (size_t)pair * a.mv_plane);
   const int lane = threadIdx.x & 31;
   if ((gw & 3) == 0 && (a.mv_plane & 3) == 0) {
+    // One thread = a strip of 4 x 4 blocks: six 128-bit row loads (rows by0 - 1 .. by0 + 4, clamped: a clamped neighbour is the
+    // block itself or another neighbour, so the test is unchanged) issued together, left / right halo entries from the
+    // neighbouring lanes by shuffle (explicit loads only at warp edges), four 128-bit stores.
     const int gw4 = gw >> 2;
-    const uint32_t groups = (uint32_t)gw4 * gh;
-    const uint32_t limit = (groups + 31u) / 32u * 32u;
+    const uint32_t strips = (uint32_t)gw4 * (uint32_t)((gh + 3) >> 2);
+    const uint32_t limit = (strips + 31u) / 32u * 32u;
     for (uint32_t t = lc.gtid; t < limit; t += lc.gthreads) {
-      uint32_t work = 0;
-      int i0 = 0;
-      if (t < groups) {
-        const int by = (int)(t / gw4), bx = (int)(t - (uint32_t)by * gw4) * 4;
-        i0 = by * gw + bx;
-        const int ru = max(by - 1, 0) * gw, rm = by * gw, rd = min(by + 1, gh - 1) * gw;
-        const int cl = max(bx - 1, 0), cr = min(bx + 4, gw - 1);
-        const uint4 U = *reinterpret_cast<const uint4*>(O + ru + bx);
-        const uint4 M = *reinterpret_cast<const uint4*>(O + rm + bx);
-        const uint4 D = *reinterpret_cast<const uint4*>(O + rd + bx);
-        const uint32_t u[6] = {O[ru + cl], U.x, U.y, U.z, U.w, O[ru + cr]};
-        const uint32_t m[6] = {O[rm + cl], M.x, M.y, M.z, M.w, O[rm + cr]};
-        const uint32_t d[6] = {O[rd + cl], D.x, D.y, D.z, D.w, O[rd + cr]};
+      const bool live = t < strips;
+      const int st = live ? (int)(t / gw4) : 0, cg = live ? (int)(t - (uint32_t)st * gw4) : 0;
+      const int bx = cg * 4, by0 = st * 4;
+      uint4 R[6];
+      int ry[6];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t k0 = m[j + 1];
-          const bool same = u[j] == k0 && u[j + 1] == k0 && u[j + 2] == k0 && m[j] == k0 && m[j + 2] == k0 && d[j] == k0 &&
-                            d[j + 1] == k0 && d[j + 2] == k0;
-          work |= same ? 0u : (1u << j);
+      for (int i = 0; i < 6; ++i) {
+        ry[i] = min(max(by0 - 1 + i, 0), gh - 1) * gw;
+        R[i] = live ? *reinterpret_cast<const uint4*>(O + ry[i] + bx) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      uint32_t Lh[6], Rh[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        Lh[i] = __shfl_up_sync(0xffffffffu, R[i].w, 1);
+        Rh[i] = __shfl_down_sync(0xffffffffu, R[i].x, 1);
+        if (cg == 0) Lh[i] = R[i].x;               // clamped: the block itself
+        else if (lane == 0 && live) Lh[i] = O[ry[i] + bx - 1];
+        if (cg == gw4 - 1) Rh[i] = R[i].w;
+        else if (lane == 31 && live) Rh[i] = O[ry[i] + bx + 4];
+      }
+      uint32_t work = 0;  // bit 4 * r + j: block (bx + j, by0 + r) has candidates that differ
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if (live && by0 + r < gh) {
+          const uint32_t u[6] = {Lh[r], R[r].x, R[r].y, R[r].z, R[r].w, Rh[r]};
+          const uint32_t m[6] = {Lh[r + 1], R[r + 1].x, R[r + 1].y, R[r + 1].z, R[r + 1].w, Rh[r + 1]};
+          const uint32_t d[6] = {Lh[r + 2], R[r + 2].x, R[r + 2].y, R[r + 2].z, R[r + 2].w, Rh[r + 2]};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t k0 = m[j + 1];
+            const bool same = u[j] == k0 && u[j + 1] == k0 && u[j + 2] == k0 && m[j] == k0 && m[j + 2] == k0 && d[j] == k0 &&
+                              d[j + 1] == k0 && d[j + 2] == k0;
+            work |= same ? 0u : (1u << (4 * r + j));
+          }
+          *reinterpret_cast<uint4*>(Y + (size_t)(by0 + r) * gw + bx) = R[r + 1];
         }
-        *reinterpret_cast<uint4*>(Y + i0) = M;
       }
       const int k = __popc(work);
       if (__ballot_sync(0xffffffffu, k > 0) == 0u) continue;
@@ -1521,8 +1603,8 @@ __device__ __forceinline__ void level_classify(const RegArgs& a, int pair, const
       base = __shfl_sync(0xffffffffu, base, 31);
       uint32_t* dst = list + base + (uint32_t)(incl - k);
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if ((work >> j) & 1u) *dst++ = (uint32_t)(i0 + j);
+      for (int q = 0; q < 16; ++q)
+        if ((work >> q) & 1u) *dst++ = (uint32_t)((by0 + (q >> 2)) * gw + bx + (q & 3));
     }
   } else {
     const uint32_t nb = (uint32_t)gw * gh;
@@ -1560,7 +1642,6 @@ template <int BSK, bool MULTI>
 __device__ __forceinline__ void level_sweep(const RegArgs& a, int pair, const LevelCtx& lc, uint32_t& ep, uint32_t& rounds,
                                             uint32_t& blocks) {
   constexpr int TEAMSZ = BSK <= 4 ? 1 : (BSK >= 32 ? 32 : 16);
-  constexpr int TPW = 32 / TEAMSZ;
   const short2* O = a.O + (size_t)pair * a.mv_plane;
   short2* Y = a.Y + (size_t)pair * a.mv_plane;
   uint32_t* Yu = reinterpret_cast<uint32_t*>(Y);
@@ -1573,9 +1654,15 @@ __device__ __forceinline__ void level_sweep(const RegArgs& a, int pair, const Le
     for (int i = 0; i < 5; ++i) lc.cnt[i] = 0;
   }
   level_sync<MULTI>();
+  // BBME_REG_PROFILE: per (level, block size) wall time of pair 0's phases in ns, words [0] classify [1] first pass [2] later
+  // rounds [3] rounds [4] listed blocks [5] blocks of later rounds [6] deferred blocks
+  uint32_t* prof = (a.hist && pair == 0 && lc.gtid == 0) ? a.hist + 8 * (31 - __clz(BSK)) : nullptr;
+  unsigned long long t0 = 0;
+  if (prof) t0 = globaltimer_ns();
   level_classify(a, pair, lc, lists[0]);
   level_sync<MULTI>();
-  const uint32_t team = lc.gtid / TEAMSZ, tl = lc.gtid % TEAMSZ, nteams = lc.gthreads / TEAMSZ;
+  if (prof) { const unsigned long long t1 = globaltimer_ns(); prof[0] += (uint32_t)(t1 - t0); t0 = t1; prof[4] += lc.cnt[0]; }
+  const uint32_t tl = lc.gtid % TEAMSZ;
   for (int r = 0;; ++r) {
     // round r reads list[r & 1] (counter r % 3), appends to list[(r + 1) & 1] (counter (r + 1) % 3) and clears counter
     // (r + 2) % 3, which was last read before the barrier that precedes this round; the deferred list's counter alternates
@@ -1591,15 +1678,33 @@ __device__ __forceinline__ void level_sweep(const RegArgs& a, int pair, const Le
     uint32_t* next_count = &lc.cnt[(r + 1) % 3];
     uint32_t* dcount = &lc.cnt[3 + (r & 1)];
     ++ep;
-    const uint32_t limit = (cnt + TPW - 1) / TPW * TPW;  // whole warps iterate together
-    for (uint32_t e = team; e < limit; e += nteams) {
-      const bool live = e < cnt;
-      const int b = (int)lcur[live ? e : cnt - 1];
-      const int bx = b % a.gw, by = b / a.gw;
-      uint32_t nv = 0;
-      bool changed;
-      if (BSK <= 4) {
-        const bool done = !live || reg_eval_small_fast<BSK>(a, pair, O, Y, bx, by, &nv);
+    if (BSK <= 4) {
+      // One thread per block, software-pipelined: the list entry is loaded two iterations ahead and the nine vectors one
+      // iteration ahead, so that an evaluation waits for ONE memory round trip (its windows) instead of three dependent
+      // ones.  Reading the vectors early is safe: a block that read a neighbour's old value is re-enqueued by that
+      // neighbour's push, whenever the read happened (chaotic iteration).
+      const uint32_t limit = (cnt + 31u) / 32u * 32u;  // whole warps iterate together
+      uint32_t e = lc.gtid;
+      int b1 = e < limit ? (int)lcur[e < cnt ? e : cnt - 1] : 0;
+      int b2 = e + lc.gthreads < limit ? (int)lcur[e + lc.gthreads < cnt ? e + lc.gthreads : cnt - 1] : 0;
+      uint32_t A1 = 0, pk1[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pk1[i] = 0;
+      if (e < limit) small_gather(a, O, Y, b1 % a.gw, b1 / a.gw, A1, pk1);
+      for (; e < limit; e += lc.gthreads) {
+        const bool live = e < cnt;
+        const int b = b1;
+        const uint32_t A0 = A1;
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[i] = pk1[i];
+        b1 = b2;
+        const uint32_t e2 = e + 2 * lc.gthreads;
+        if (e2 < limit) b2 = (int)lcur[e2 < cnt ? e2 : cnt - 1];
+        if (e + lc.gthreads < limit) small_gather(a, O, Y, b1 % a.gw, b1 / a.gw, A1, pk1);
+        const int bx = b % a.gw, by = b / a.gw;
+        uint32_t nv = 0;
+        const bool done = !live || reg_eval_small_fast<BSK>(a, pair, bx, by, A0, pk, &nv);
         const uint32_t dm = __ballot_sync(0xffffffffu, !done);
         if (dm) {
           uint32_t dbase = 0;
@@ -1608,19 +1713,50 @@ __device__ __forceinline__ void level_sweep(const RegArgs& a, int pair, const Le
           dbase = __shfl_sync(0xffffffffu, dbase, leader);
           if (!done) dlist[dbase + __popc(dm & ((1u << lane) - 1u))] = (uint32_t)b;
         }
-        changed = live && done && nv != Yu[b];
-      } else {
-        nv = reg_eval_team_lean<BSK>(a, pair, O, Y, bx, by, (int)tl, live);
-        changed = tl == 0 && live && nv != Yu[b];
+        const bool changed = live && done && nv != Yu[b];
+        if (changed) Yu[b] = nv;
+        push_dependents(changed, bx, by, a.gw, a.gh, stamp, ep, lnext, next_count);
       }
-      if (changed) Yu[b] = nv;
-      push_dependents(changed, bx, by, a.gw, a.gh, stamp, ep, lnext, next_count);
+    } else {
+      // A team per block.  A warp takes 32 consecutive list entries with one coalesced load; each of its teams walks through
+      // its share in list (= raster) order, loading the next block's nine vectors -- one per lane -- while the current block's
+      // windows are in flight.  The list is in raster order, so the next block is usually the right-hand neighbour: its "L"
+      // vector is patched with the value just computed (an in-place sweep along the row inside a batch, as in the reference).
+      const uint32_t nsb = (cnt + 31u) / 32u;
+      const uint32_t warp_g = lc.gtid >> 5, nwarps = lc.gthreads >> 5;
+      const int base = lane - (int)tl;
+      for (uint32_t sb = warp_g; sb < nsb; sb += nwarps) {
+        const uint32_t e0 = sb * 32u;
+        const uint32_t mine = e0 + (uint32_t)lane;
+        const uint32_t entry = lcur[mine < cnt ? mine : cnt - 1];
+        int bn = (int)__shfl_sync(0xffffffffu, entry, base);
+        bool vn = false;
+        uint32_t myn = team_slot_load(a, O, Y, bn % a.gw, bn / a.gw, (int)tl, vn);
+#pragma unroll 1
+        for (int k = 0; k < TEAMSZ; ++k) {
+          const int b = bn;
+          const uint32_t my = myn;
+          const bool valid = vn;
+          const bool live = e0 + (uint32_t)(base + k) < cnt;
+          if (k + 1 < TEAMSZ) {
+            bn = (int)__shfl_sync(0xffffffffu, entry, base + k + 1);
+            myn = team_slot_load(a, O, Y, bn % a.gw, bn / a.gw, (int)tl, vn);
+          }
+          const int bx = b % a.gw, by = b / a.gw;
+          const uint32_t nv = reg_eval_team_lean<BSK>(a, pair, bx, by, (int)tl, live, my, valid);
+          const bool changed = tl == 0 && live && nv != Yu[b];
+          if (changed) Yu[b] = nv;
+          if (tl == 1 && live && vn && bn == b + 1) myn = nv;  // the next block's left neighbour is this block
+          push_dependents(changed, bx, by, a.gw, a.gh, stamp, ep, lnext, next_count);
+        }
+      }
     }
     if (BSK <= 4) {
       // second pass of the round: the blocks with three or more distinct candidate vectors
       if (MULTI) __threadfence();
       level_sync<MULTI>();
       const uint32_t dcnt = *reinterpret_cast<volatile uint32_t*>(dcount);
+      if (prof) prof[6] += dcnt;
       const uint32_t dlimit = (dcnt + 31u) / 32u * 32u;
       for (uint32_t e = lc.gtid; e < dlimit; e += lc.gthreads) {
         const bool live = e < dcnt;
@@ -1638,6 +1774,12 @@ __device__ __forceinline__ void level_sweep(const RegArgs& a, int pair, const Le
     }
     if (MULTI) __threadfence();
     level_sync<MULTI>();
+    if (prof) {
+      const unsigned long long t1 = globaltimer_ns();
+      prof[r == 0 ? 1 : 2] += (uint32_t)(t1 - t0);
+      t0 = t1;
+      if (r > 0) { prof[3] += 1; prof[5] += cnt; }
+    }
   }
 }
 

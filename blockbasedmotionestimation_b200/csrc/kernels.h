@@ -51,8 +51,12 @@ void launch_export_subsample(const short2* mv2, int gw2, size_t mv_plane, int pa
 void launch_pyrdown(ImgView src1, ImgView src2, uint8_t* dst1, uint8_t* dst2, int dpitch, size_t dplane, int n,
                     cudaStream_t s);
 // generic exhaustive search (any power-of-two block size); mv holds the prediction on entry
+// variant: 0 = find_min_block_spiral (the reference's active search), 1 = find_min_block (raster scan, L1-distance tie-break)
 void launch_search_generic(ImgView i1, ImgView i2, MvView mv, int bs, int R, int n, unsigned long long* counters,
-                           cudaStream_t s);
+                           cudaStream_t s, int variant = 0);
+// MF::draw_MVimage: motion-compensated frame from image 2 and a block-granular field
+void launch_compensate(ImgView i2, const short2* mv, int gw, size_t mv_plane, int bs, uint8_t* out, int out_pitch,
+                       size_t out_plane, int n, cudaStream_t s);
 // MF::copyMVs: coarse final field at 2x2 granularity -> fine prediction at fine block granularity
 void launch_copy_mvs(const short2* coarse, int cgw2, size_t cplane, int cbs, MvView fine, int fbs, int n,
                      cudaStream_t s);

@@ -81,6 +81,9 @@ typedef struct {
   int search_kernel;   /* 0 = auto, 1 = force the generic kernel, 2 = force the TMA kernel (error if unsupported) */
   int collect_stats;   /* 1 = per-stage CUDA-event timing + work counters (adds synchronisation) */
   int keep_search_mv;  /* 1 = keep a copy of every level's field after the search (for bbme_debug_level_mv) */
+  int search_variant;  /* 0 = MF::find_min_block_spiral, the search the reference runs (motion_framework.cpp:236);
+                          1 = MF::find_min_block (:246-294), the raster-scan search with the L1-distance tie-break that the
+                              commented line :235 would call instead (generic kernel; +-R up to 180) */
 } bbme_options;
 
 void bbme_default_options(bbme_options* o);
@@ -236,6 +239,13 @@ int bbme_stage_resize(bbme_ctx* ctx, const uint8_t* src, int w, int h, int facto
  * prediction on entry and the result on exit.  kernel: as bbme_options.search_kernel. */
 int bbme_stage_search(bbme_ctx* ctx, const uint8_t* im1, const uint8_t* im2, int w, int h, int block_size,
                       int search_size, int16_t* mv, int kernel, bbme_stats* st);
+/* MF::calcLevelBM with MF::find_min_block (motion_framework.cpp:246-294) instead of the spiral search: same arguments. */
+int bbme_stage_search_raster(bbme_ctx* ctx, const uint8_t* im1, const uint8_t* im2, int w, int h, int block_size,
+                             int search_size, int16_t* mv);
+/* MF::draw_MVimage (motion_framework.cpp:887-905): the motion-compensated frame -- each block_size x block_size block of im2 at
+ * (block position + vector) copied to the block's position in out (w x h bytes, zero where the source leaves the image).
+ * mv: (h/bs) x (w/bs) x 2 int16.  After calcMotionBlockMatching the reference would call it with block_size 2 (:205,213-216). */
+int bbme_stage_compensate(bbme_ctx* ctx, const uint8_t* im2, int w, int h, int block_size, const int16_t* mv, uint8_t* out);
 /* One MF::regularize_MVs sweep (motion_framework.cpp:424-530) with in-place raster semantics.
  * lambda is the level's current lambda, lambda_multiplier the sweep's multiplier (motion_framework.cpp:607). */
 int bbme_stage_regularize(bbme_ctx* ctx, const uint8_t* im1, const uint8_t* im2, int w, int h, int block_size,

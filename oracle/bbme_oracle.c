@@ -35,6 +35,7 @@
 #include "bbme_oracle.h"
 
 #include <float.h>
+#include <limits.h>
 #include <math.h>
 #include <pthread.h>
 #include <stdio.h>
@@ -237,6 +238,59 @@ void orc_search_level(const uint8_t* im1, const uint8_t* im2, int w, int h, int 
   }
 }
 
+/* MF::find_min_block (motion_framework.cpp:246-294): the raster-scan full search that calcLevelBM's commented line :235 would
+ * call instead of the spiral search.  The window is clamped to the image (:260,262; no centre test), the scan is row-major,
+ * a strictly smaller SAD wins (:271), and at equal SAD the candidate with the smaller L1 distance to the block's position in
+ * image 1 (:278).  With an empty window the predicted position is returned unchanged (:251-252). */
+static pos2i raster_search(const uint8_t* im1, const uint8_t* im2, int w, int h, int bs, int ss, int y1, int x1, int y2,
+                           int x2) {
+  int start_pos = (ss - bs) >> 1;
+  int sad_min = INT_MAX, l1_dist = INT_MAX;
+  pos2i best;
+  best.x = x2;
+  best.y = y2;
+  int k0 = y2 - start_pos > 0 ? y2 - start_pos : 0, k1 = h - bs + 1 < y2 + start_pos + 1 ? h - bs + 1 : y2 + start_pos + 1;
+  int l0 = x2 - start_pos > 0 ? x2 - start_pos : 0, l1 = w - bs + 1 < x2 + start_pos + 1 ? w - bs + 1 : x2 + start_pos + 1;
+  for (int k = k0; k < k1; ++k) {
+    for (int l = l0; l < l1; ++l) {
+      int sad = sad_block(im1 + (size_t)y1 * w + x1, im2 + (size_t)k * w + l, w, bs);
+      int dist = abs(x1 - l) + abs(y1 - k);
+      if (sad < sad_min) {
+        sad_min = sad; best.x = l; best.y = k; l1_dist = dist;
+      } else if (sad == sad_min && dist < l1_dist) {
+        best.x = l; best.y = k; l1_dist = dist;
+      }
+    }
+  }
+  return best;
+}
+
+void orc_search_level_raster(const uint8_t* im1, const uint8_t* im2, int w, int h, int bs, int ss, float* flow) {
+  for (int i = 0; i < h; i += bs) {
+    for (int j = 0; j < w; j += bs) { /* calcLevelBM, :229-239, with :235 instead of :236 */
+      float* f = flow + ((size_t)i * w + j) * 2;
+      int x2 = j + (int)f[0];
+      int y2 = i + (int)f[1];
+      pos2i r = raster_search(im1, im2, w, h, bs, ss, i, j, y2, x2);
+      f[0] = (float)r.x - (float)j;
+      f[1] = (float)r.y - (float)i;
+    }
+  }
+}
+
+/* MF::draw_MVimage (motion_framework.cpp:887-905): the motion-compensated frame -- every block of image 2 at (block position +
+ * vector) copied to the block's position; blocks whose source leaves the image are skipped (out keeps the caller's bytes). */
+void orc_compensate(const uint8_t* im2, int w, int h, int bs, const float* flow, uint8_t* out) {
+  for (int i = 0; i < h; i += bs) {
+    for (int j = 0; j < w; j += bs) {
+      int x2 = j + (int)flow[((size_t)i * w + j) * 2];
+      int y2 = i + (int)flow[((size_t)i * w + j) * 2 + 1];
+      if (x2 < 0 || x2 > w - bs || y2 < 0 || y2 > h - bs) continue;
+      for (int r = 0; r < bs; ++r) memcpy(out + (size_t)(i + r) * w + j, im2 + (size_t)(y2 + r) * w + x2, (size_t)bs);
+    }
+  }
+}
+
 /* ------------------------------------------------------------------ regularisation (motion_framework.cpp:424-662) */
 
 typedef struct { float u, v; } mv2f;
@@ -393,10 +447,10 @@ void orc_copy_to_all_pixels(int w, int h, int bs, float* flow) {
 
 /* ------------------------------------------------------------------ whole pair */
 
-int orc_estimate_debug(const uint8_t* im1, const uint8_t* im2, int w, int h, size_t pitch, int levels,
-                       const int* search_size, const int* block_size, int sweeps, float* flow_out, orc_stats* st,
-                       uint8_t* const* pyr1, uint8_t* const* pyr2, float* const* after_search,
-                       float* const* after_reg) {
+static int estimate_impl(const uint8_t* im1, const uint8_t* im2, int w, int h, size_t pitch, int levels,
+                         const int* search_size, const int* block_size, int sweeps, float* flow_out, orc_stats* st,
+                         uint8_t* const* pyr1, uint8_t* const* pyr2, float* const* after_search,
+                         float* const* after_reg, int raster_search_variant) {
   orc_shape sh;
   orc_stats local;
   if (!st) st = &local;
@@ -436,7 +490,8 @@ int orc_estimate_debug(const uint8_t* im1, const uint8_t* im2, int w, int h, siz
       int lw = sh.level_w[l], lh = sh.level_h[l];
       size_t fbytes = (size_t)lw * lh * 2 * sizeof(float);
       if (l != levels - 1) orc_copy_mvs(fl[l + 1], sh.level_w[l + 1], sh.level_h[l + 1], block_size[l + 1], fl[l]);
-      orc_search_level(i1[l], i2[l], lw, lh, block_size[l], search_size[l], fl[l], st, l);
+      if (raster_search_variant) orc_search_level_raster(i1[l], i2[l], lw, lh, block_size[l], search_size[l], fl[l]);
+      else orc_search_level(i1[l], i2[l], lw, lh, block_size[l], search_size[l], fl[l], st, l);
       if (after_search && after_search[l]) memcpy(after_search[l], fl[l], fbytes);
       int bs = block_size[l];
       float lambda = (float)(block_size[l] / 2); /* integer division, :73,95 */
@@ -458,6 +513,20 @@ int orc_estimate_debug(const uint8_t* im1, const uint8_t* im2, int w, int h, siz
     free(fl[l]);
   }
   return rc;
+}
+
+int orc_estimate_debug(const uint8_t* im1, const uint8_t* im2, int w, int h, size_t pitch, int levels,
+                       const int* search_size, const int* block_size, int sweeps, float* flow_out, orc_stats* st,
+                       uint8_t* const* pyr1, uint8_t* const* pyr2, float* const* after_search,
+                       float* const* after_reg) {
+  return estimate_impl(im1, im2, w, h, pitch, levels, search_size, block_size, sweeps, flow_out, st, pyr1, pyr2, after_search,
+                       after_reg, 0);
+}
+
+/* The whole path with find_min_block (:246-294) in calcLevelBM, i.e. with the comment markers of :235 and :236 swapped. */
+int orc_estimate_raster(const uint8_t* im1, const uint8_t* im2, int w, int h, size_t pitch, int levels,
+                        const int* search_size, const int* block_size, int sweeps, float* flow_out) {
+  return estimate_impl(im1, im2, w, h, pitch, levels, search_size, block_size, sweeps, flow_out, NULL, NULL, NULL, NULL, NULL, 1);
 }
 
 int orc_estimate(const uint8_t* im1, const uint8_t* im2, int w, int h, size_t pitch, int levels,

@@ -69,6 +69,14 @@ int orc_spiral_rank(int dx, int dy);
 void orc_search_level(const uint8_t* im1, const uint8_t* im2, int w, int h, int block_size, int search_size,
                       float* flow, orc_stats* st, int level);
 
+/* MF::calcLevelBM with MF::find_min_block (motion_framework.cpp:246-294, the raster-scan search with the L1-distance tie-break
+ * that the commented line :235 would call).  Pinned against the reference's own function through oracle/_ref. */
+void orc_search_level_raster(const uint8_t* im1, const uint8_t* im2, int w, int h, int block_size, int search_size, float* flow);
+
+/* MF::draw_MVimage, motion_framework.cpp:887-905: motion-compensated frame from image 2 and the field at block corners;
+ * blocks whose source leaves the image keep the bytes already in `out`. */
+void orc_compensate(const uint8_t* im2, int w, int h, int block_size, const float* flow, uint8_t* out);
+
 /* One MF::regularize_MVs sweep in place, motion_framework.cpp:424-530. */
 void orc_regularize_sweep(const uint8_t* im1, const uint8_t* im2, int w, int h, int block_size, float lambda,
                           int lambda_multiplier, float* flow, orc_stats* st, int level);
@@ -86,6 +94,10 @@ void orc_copy_to_all_pixels(int w, int h, int block_size, float* flow);
  * sweeps = regularisation sweeps per block size (reference hard-codes 2, motion_framework.cpp:143,184). */
 int orc_estimate(const uint8_t* im1, const uint8_t* im2, int w, int h, size_t pitch, int levels,
                  const int* search_size, const int* block_size, int sweeps, float* flow_out, orc_stats* st);
+
+/* The whole path with MF::find_min_block (raster scan) as the per-level search instead of the spiral search. */
+int orc_estimate_raster(const uint8_t* im1, const uint8_t* im2, int w, int h, size_t pitch, int levels,
+                        const int* search_size, const int* block_size, int sweeps, float* flow_out);
 
 /* Same, additionally copying the state after each stage into caller buffers (any may be NULL):
  *   pyr1/pyr2[l]   : level images (dense level_w x level_h)

@@ -43,12 +43,15 @@ def load():
         lib.orc_estimate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_void_p,
                                      C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         lib.orc_estimate_debug.argtypes = lib.orc_estimate.argtypes + [C.c_void_p] * 4
+        lib.orc_estimate_raster.argtypes = lib.orc_estimate.argtypes[:-1]
         lib.orc_estimate_many.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int,
                                           C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         lib.orc_pad_image.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
         lib.orc_pyrdown.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         lib.orc_search_level.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                          C.c_void_p, C.c_int]
+        lib.orc_search_level_raster.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        lib.orc_compensate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         lib.orc_divide_blocks.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
         lib.orc_copy_mvs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         lib.orc_copy_to_all_pixels.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
@@ -144,6 +147,23 @@ def estimate(im1, im2, search_size, block_size, sweeps=2, debug=False):
     return flow, stats_dict(st), {"pyr1": pyr1, "pyr2": pyr2, "after_search": a_s, "after_reg": a_r, "shape": sh}
 
 
+def estimate_raster(im1, im2, search_size, block_size, sweeps=2):
+    """Whole pair with find_min_block (raster scan, L1-distance tie-break) as the per-level search."""
+    lib = load()
+    im1 = np.ascontiguousarray(im1, np.uint8)
+    im2 = np.ascontiguousarray(im2, np.uint8)
+    h, w = im1.shape
+    rc, sh = plan_shape(w, h, block_size)
+    if rc != 0:
+        raise ValueError(f"oracle plan_shape failed: {rc}")
+    flow = np.empty((sh["padded_height"], sh["padded_width"], 2), np.float32)
+    rc = lib.orc_estimate_raster(im1.ctypes.data, im2.ctypes.data, w, h, w, len(block_size), _ia(search_size), _ia(block_size),
+                                 sweeps, flow.ctypes.data)
+    if rc != 0:
+        raise ValueError(f"oracle estimate_raster failed: {rc}")
+    return flow
+
+
 def estimate_many(pairs, search_size, block_size, sweeps=2, threads=1):
     lib = load()
     n = len(pairs)
@@ -173,6 +193,28 @@ def search_level(im1, im2, block_size, search_size, flow):
     st = OrcStats()
     lib.orc_search_level(im1.ctypes.data, im2.ctypes.data, w, h, block_size, search_size, flow.ctypes.data, C.byref(st), 0)
     return flow, stats_dict(st)
+
+
+def search_level_raster(im1, im2, block_size, search_size, flow):
+    """calcLevelBM with find_min_block (motion_framework.cpp:246-294): raster scan, L1-distance tie-break."""
+    lib = load()
+    im1 = np.ascontiguousarray(im1, np.uint8)
+    im2 = np.ascontiguousarray(im2, np.uint8)
+    h, w = im1.shape
+    flow = np.ascontiguousarray(flow, np.float32).copy()
+    lib.orc_search_level_raster(im1.ctypes.data, im2.ctypes.data, w, h, block_size, search_size, flow.ctypes.data)
+    return flow
+
+
+def compensate(im2, block_size, flow):
+    """draw_MVimage (motion_framework.cpp:887-905) into a zero-filled frame."""
+    lib = load()
+    im2 = np.ascontiguousarray(im2, np.uint8)
+    h, w = im2.shape
+    flow = np.ascontiguousarray(flow, np.float32)
+    out = np.zeros((h, w), np.uint8)
+    lib.orc_compensate(im2.ctypes.data, w, h, block_size, flow.ctypes.data, out.ctypes.data)
+    return out
 
 
 def regularize_sweep(im1, im2, block_size, lam, mult, flow):
@@ -277,6 +319,8 @@ def load_ref():
         lib.ref_flow_mse.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         lib.ref_flow_mse.restype = C.c_double
         lib.ref_flow_color.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]
+        lib.ref_find_min_block_level.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        lib.ref_draw_mvimage.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _ref = lib
     return _ref
 
@@ -313,4 +357,35 @@ def ref_flow_color(flow, maxmotion=-1.0):
     rc = lib.ref_flow_color(flow.ctypes.data, w, h, C.c_float(maxmotion), out.ctypes.data)
     if rc != 0:
         raise RuntimeError("ref_flow_color failed")
+    return out
+
+
+def ref_search_level_raster(im1, im2, block_size, search_size, flow):
+    """The reference's own find_min_block (:246-294) driven block by block like calcLevelBM; None without oracle/_ref."""
+    lib = load_ref()
+    if lib is None:
+        return None
+    im1 = np.ascontiguousarray(im1, np.uint8)
+    im2 = np.ascontiguousarray(im2, np.uint8)
+    h, w = im1.shape
+    flow = np.ascontiguousarray(flow, np.float32).copy()
+    rc = lib.ref_find_min_block_level(im1.ctypes.data, im2.ctypes.data, w, h, block_size, search_size, flow.ctypes.data)
+    if rc != 0:
+        raise ValueError("ref_find_min_block_level: the size must be a multiple of the block size")
+    return flow
+
+
+def ref_compensate(im1, im2, block_size, flow):
+    """The reference's own draw_MVimage (:887-905) into a zero-filled frame; None without oracle/_ref."""
+    lib = load_ref()
+    if lib is None:
+        return None
+    im1 = np.ascontiguousarray(im1, np.uint8)
+    im2 = np.ascontiguousarray(im2, np.uint8)
+    h, w = im2.shape
+    flow = np.ascontiguousarray(flow, np.float32)
+    out = np.zeros((h, w), np.uint8)
+    rc = lib.ref_draw_mvimage(im1.ctypes.data, im2.ctypes.data, w, h, block_size, flow.ctypes.data, out.ctypes.data)
+    if rc != 0:
+        raise ValueError("ref_draw_mvimage: the size must be a multiple of the block size")
     return out

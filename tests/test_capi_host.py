@@ -243,3 +243,27 @@ def test_pool_and_mf_cache_fail_loudly_without_a_gpu():
     rc = lib.bbme_mf_open(C.byref(ctx), 0, 64, 64, 1, (C.c_int * 1)(16), (C.c_int * 1)(8), 2, None)
     assert rc == -6 and not ctx.value
     lib.bbme_mf_cache_clear()
+
+
+def test_color_flow_cli(tmp_path):
+    """tools/color_flow == the vendored Middlebury tool's command line (middlebury/flow-code/color_flow.cpp:68-98): same console
+    line, a PNG whose pixels are Flow::MotionToColor's (itself pinned to the reference's function by flow_color_ref.npz)."""
+    cv2 = pytest.importorskip("cv2")
+    exe = os.path.join(ROOT, "tools", "color_flow")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", ROOT, "tools/color_flow"], stdout=subprocess.DEVNULL)
+    fl = bb.Flow()
+    rng = np.random.default_rng(5)
+    f = (rng.standard_normal((37, 53, 2)) * 6).astype(np.float32)
+    f[3:6, 4:9] = 1e10  # unknown flow -> black
+    src = tmp_path / "in.flo"
+    fl.WriteFlowFile(f, src)
+    for extra, maxmotion in ([], -1.0), (["7.5"], 7.5):
+        out = tmp_path / "out.png"
+        res = subprocess.run([exe, "-quiet", str(src), str(out)] + extra, capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
+        assert res.stdout.startswith("max motion: ") and "motion range: u = " in res.stdout and res.stderr == ""
+        assert np.array_equal(cv2.imread(str(out), cv2.IMREAD_COLOR), fl.MotionToColor(f, maxmotion))
+    res = subprocess.run([exe, str(src), str(tmp_path / "out.ppm")], capture_output=True, text=True)
+    assert res.returncode == 0 and "normalizing by" in res.stderr
+    assert subprocess.run([exe, str(src)], capture_output=True).returncode != 0  # usage error

@@ -230,3 +230,23 @@ def test_oracle_fuzz_against_live_reference(oracle):
         got, _ = oracle.estimate(f1, f2, ss, bs, 2)
         assert np.array_equal(got, want), (w, h, ss, bs, kind)
         done += 1
+
+
+def test_raster_search_and_compensation_equal_the_references_own_functions(oracle):
+    """the oracle's find_min_block (:246-294) and draw_MVimage (:887-905) restatements against the reference's
+    own (uncalled) member functions, run through oracle/_ref."""
+    if oracle.load_ref() is None:
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(11)
+    differs = 0
+    for (h, w, bs, ss, kind) in [(64, 96, 8, 24, "textured"), (64, 64, 16, 32, "textured"), (48, 80, 4, 10, "noise"),
+                                 (64, 96, 8, 24, "constant"), (96, 128, 32, 48, "textured"), (40, 56, 2, 6, "textured")]:
+        f1, f2 = make_pair(h, w, int(rng.integers(1 << 20)), shift=(2, -1), kind=kind)
+        pred = np.zeros((h, w, 2), np.float32)
+        pred[::bs, ::bs] = rng.integers(-12, 13, (h // bs, w // bs, 2)).astype(np.float32)  # some predictions leave the image
+        got = oracle.search_level_raster(f1, f2, bs, ss, pred)
+        assert np.array_equal(got, oracle.ref_search_level_raster(f1, f2, bs, ss, pred)), (h, w, bs, ss, kind)
+        assert np.array_equal(oracle.compensate(f2, bs, got), oracle.ref_compensate(f1, f2, bs, got))
+        spiral, _ = oracle.search_level(f1, f2, bs, ss, pred)
+        differs += int((spiral[::bs, ::bs] != got[::bs, ::bs]).any(-1).sum())
+    assert differs > 0  # the two searches are different algorithms (tie-break, no centre test)
