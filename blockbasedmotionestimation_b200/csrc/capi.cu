@@ -312,7 +312,7 @@ int run_chunk(bbme_ctx* c, Slot& s, int n, const uint8_t* d_in1, const uint8_t* 
       ra.wl_plane = c->cap[0];
       ra.ctr = s.ctr;
       ra.hist = s.hist ? s.hist + 64 * l : nullptr;  // BBME_REG_PROFILE: 8 words per block size, 64 per level
-      if (launch_reg_level(ra, c->opt.sweeps, lambda, 1, 0, n, c->sm_count, st) != 0)
+      if (launch_reg_level(ra, c->opt.sweeps, lambda, 1, 0, n, c->sm_count / (int)c->slots.size(), st) != 0)
         return fail(c, BBME_E_CUDA, "regularisation kernel launch failed at level %d: %s", l, cudaGetErrorString(cudaGetLastError()));
       ++c->launches;
       int swaps = 0;
@@ -507,15 +507,16 @@ void CUDART_CB expand_cb(void* p) {
 int enqueue_dense_result(bbme_ctx* c, Slot& s, int m, float* const* flow) {
   const size_t plane = c->cap[0] * 2;  // int16 per pair
   const int turn = s.stage_turn;
-  if (!s.stage[turn]) {
+  for (int j = 0; j < 2; ++j) {  // first host-buffer call on this slot: both staging buffers at once (pinning is slow)
+    if (s.stage[j]) continue;
     void* q = nullptr;
     const size_t bytes = (size_t)c->opt.chunk_pairs * plane * sizeof(int16_t);
     if (cudaHostAlloc(&q, bytes, cudaHostAllocDefault) != cudaSuccess) {
       cudaGetLastError();
       return fail(c, BBME_E_NOMEM, "cudaHostAlloc(%zu bytes) for the result staging buffer failed", bytes);
     }
-    s.stage[turn] = static_cast<int16_t*>(q);
-    s.ticket[turn] = new Ticket();
+    s.stage[j] = static_cast<int16_t*>(q);
+    s.ticket[j] = new Ticket();
   }
   s.ticket[turn]->wait();  // the chunk that used this staging buffer two turns ago has been expanded
   CUDA_TRY(c, cudaMemcpyAsync(s.stage[turn], s.mv_final[0], (size_t)m * plane * sizeof(int16_t), cudaMemcpyDeviceToHost, s.stream));

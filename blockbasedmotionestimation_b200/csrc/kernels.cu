@@ -1256,10 +1256,6 @@ __device__ __forceinline__ uint32_t sad_small(const uint32_t* A, const uint8_t* 
   }
 }
 
-// One thread per 2x2 / 4x4 block, blocks whose candidates hold at most two distinct vectors A (the block's own, index 0)
-// and B: S_A = (#B) * d(A, B), S_B = (#A) * d(A, B) (integer-valued, exact in float like the reference's running sum),
-// B wins iff E_B < E_A (strict: index 0 wins ties, :653-659).  Returns false if there are more than two distinct vectors
-// (the caller defers the block to the nine-slot evaluator); *out = the block's new vector otherwise.
 // The nine candidate vectors of block (bx, by), packed: A0 = the block's own (slot 0), pk[0..7] = slots 1..8
 // [L, R, DR, UL, UR, U, D, DL]; a missing neighbour holds A0 (it drops out of every count below).  Split from the evaluation so
 // that the caller can issue these loads one iteration ahead (the evaluation's only other memory round trip is the windows).
@@ -1281,59 +1277,170 @@ __device__ __forceinline__ void small_gather(const RegArgs& a, const short2* O, 
   pk[7] = Ou[(dn && lf) ? idx + gw - 1 : idx];
 }
 
-template <int BS>
-__device__ __forceinline__ bool reg_eval_small_fast(const RegArgs& a, int pair, int bx, int by, uint32_t A0, uint32_t (&pk)[8],
-                                                    uint32_t* out) {
-  const int gw = a.gw, gh = a.gh;
-  const bool up = by > 0, dn = by < gh - 1, lf = bx > 0, rt = bx < gw - 1;
-  // a missing neighbour was read from the block's own index (possibly from the NEW field): it counts as A
-  pk[0] = lf ? pk[0] : A0;
-  pk[1] = rt ? pk[1] : A0;
-  pk[2] = (dn && rt) ? pk[2] : A0;
-  pk[3] = (up && lf) ? pk[3] : A0;
-  pk[4] = (up && rt) ? pk[4] : A0;
-  pk[5] = up ? pk[5] : A0;
-  pk[6] = dn ? pk[6] : A0;
-  pk[7] = (dn && lf) ? pk[7] : A0;
-  uint32_t B = A0;
+// SAD of one row of W bytes (8 or 16) of the block (a: aligned) against the window row at b (any alignment), added to acc.  The
+// window row is fetched as the two aligned vectors that contain it; the wanted words are selected by the start offset.
+template <int W>
+__device__ __forceinline__ uint32_t row_sad(const uint8_t* a, const uint8_t* b, uint32_t acc) {
+  const uintptr_t ab = reinterpret_cast<uintptr_t>(b);
+  if (W == 8) {
+    const uint2 A = __ldg(reinterpret_cast<const uint2*>(a));
+    const uint2* q = reinterpret_cast<const uint2*>(ab & ~(uintptr_t)7);
+    const uint32_t off = (uint32_t)(ab & 7);
+    const uint2 q0 = __ldg(q), q1 = __ldg(q + 1);
+    const bool w1 = (off & 4u) != 0u;
+    const uint32_t sh = (off & 3u) * 8u;
+    const uint32_t a0 = w1 ? q0.y : q0.x, a1 = w1 ? q1.x : q0.y, a2 = w1 ? q1.y : q1.x;
+    return sad4(A.y, __funnelshift_r(a1, a2, sh), sad4(A.x, __funnelshift_r(a0, a1, sh), acc));
+  } else {
+    const uint4 A = __ldg(reinterpret_cast<const uint4*>(a));
+    const uint4* q = reinterpret_cast<const uint4*>(ab & ~(uintptr_t)15);
+    const uint32_t off = (uint32_t)(ab & 15);
+    const uint4 q0 = __ldg(q), q1 = __ldg(q + 1);
+    const bool s2 = (off & 8u) != 0u, s1 = (off & 4u) != 0u;
+    const uint32_t sh = (off & 3u) * 8u;
+    const uint32_t t0 = s2 ? q0.z : q0.x, t1 = s2 ? q0.w : q0.y, t2 = s2 ? q1.x : q0.z, t3 = s2 ? q1.y : q0.w,
+                   t4 = s2 ? q1.z : q1.x, t5 = s2 ? q1.w : q1.y;
+    const uint32_t a0 = s1 ? t1 : t0, a1 = s1 ? t2 : t1, a2 = s1 ? t3 : t2, a3 = s1 ? t4 : t3, a4 = s1 ? t5 : t4;
+    acc = sad4(A.x, __funnelshift_r(a0, a1, sh), acc);
+    acc = sad4(A.y, __funnelshift_r(a1, a2, sh), acc);
+    acc = sad4(A.z, __funnelshift_r(a2, a3, sh), acc);
+    return sad4(A.w, __funnelshift_r(a3, a4, sh), acc);
+  }
+}
+
+// SAD of the whole block at blk (image 1) against the window at win (image 2), one thread
+template <int BSK>
+__device__ __forceinline__ uint32_t block_sad_thread(const uint8_t* blk, const uint8_t* win, int pitch, int bs) {
+  if (BSK <= 4) {
+    uint32_t Ab[BSK == 2 ? 1 : 4];
+    if (BSK == 2) {
+      Ab[0] = (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(blk)) | ((uint32_t)__ldg(reinterpret_cast<const uint16_t*>(blk + pitch)) << 16);
+    } else {
 #pragma unroll
-  for (int i = 7; i >= 0; --i) B = (pk[i] != A0) ? pk[i] : B;  // the lowest slot that differs
-  *out = A0;
-  if (B == A0) return true;  // all candidates identical: index 0 wins
-  int nB = 0;
+      for (int r = 0; r < (BSK == 2 ? 1 : 4); ++r) Ab[r] = __ldg(reinterpret_cast<const uint32_t*>(blk + (size_t)r * pitch));
+    }
+    return sad_small<BSK <= 2 ? 2 : 4>(Ab, win, pitch);
+  } else if (BSK == 8) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc = row_sad<8>(blk + (size_t)r * pitch, win + (size_t)r * pitch, acc);
+    return acc;
+  } else {
+    uint32_t acc = 0;
+    const int chunks = BSK == 16 ? 1 : bs / 16;
+    const int rows = BSK == 16 ? 16 : bs;
+#pragma unroll 4
+    for (int r = 0; r < rows; ++r)
+      for (int ch = 0; ch < chunks; ++ch) acc = row_sad<16>(blk + (size_t)r * pitch + 16 * ch, win + (size_t)r * pitch + 16 * ch, acc);
+    return acc;
+  }
+}
+
+// One thread per block, any block size, for blocks whose nine candidates hold at most THREE distinct vectors u0 (the block's
+// own, slot 0), u1, u2 in order of first appearance -- a listed block sits on the border between two or three motion layers, so
+// this is nearly all of them.  With multiplicities m_k over the slots that have a neighbour: S_j = sum_k m_k * d(u_j, u_k)
+// (:637-641; integer-valued, exact in float like the reference's running sum), E_j = (float)SAD_j + (lambda * mult) * S_j (:607,
+// un-fused), FLT_MAX outside the image (:578-582); the smallest energy wins and ties go to the earlier first appearance, which is
+// the reference's scan with strict '<' (:653-659) because slots with the same vector have the same energy.  Returns false if a
+// fourth distinct vector shows up and any_count is false (the caller defers the block to a second pass that allows any count, so
+// that the warps of the first pass stay converged); *out = the new vector otherwise.
+template <int BSK>
+__device__ __forceinline__ bool reg_eval_thread(const RegArgs& a, int pair, int bx, int by, uint32_t A0, const uint32_t (&pkin)[8],
+                                                uint32_t* out, bool any_count, uint32_t* s_u) {
+  const int gw = a.gw, gh = a.gh, bs = BSK >= 32 ? a.bs : BSK;
+  const bool up = by > 0, dn = by < gh - 1, lf = bx > 0, rt = bx < gw - 1;
+  const bool has[8] = {lf, rt, dn && rt, up && lf, up && rt, up, dn, dn && lf};  // slots 1..8: L, R, DR, UL, UR, U, D, DL
+  uint32_t u1 = A0, u2 = A0;
+  int n = 1, m0 = 1, m1 = 0, m2 = 0;
   bool more = false;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    nB += (pk[i] == B) ? 1 : 0;
-    more = more || (pk[i] != A0 && pk[i] != B);
+    const uint32_t v = pkin[i];
+    if (has[i]) {  // a missing neighbour is not a candidate (its slot was read from the block's own index)
+      if (v == A0) {
+        ++m0;
+      } else if (n >= 2 && v == u1) {
+        ++m1;
+      } else if (n >= 3 && v == u2) {
+        ++m2;
+      } else if (n == 1) {
+        u1 = v; m1 = 1; n = 2;
+      } else if (n == 2) {
+        u2 = v; m2 = 1; n = 3;
+      } else {
+        more = true;
+      }
+    }
   }
-  if (more) return false;
-  const int n_valid = 1 + (lf ? 1 : 0) + (rt ? 1 : 0) + ((dn && rt) ? 1 : 0) + ((up && lf) ? 1 : 0) + ((up && rt) ? 1 : 0) +
-                      (up ? 1 : 0) + (dn ? 1 : 0) + ((dn && lf) ? 1 : 0);
-  const int nA = n_valid - nB;
-  const int ax = mv_x(A0), ay = mv_y(A0), bxv = mv_x(B), byv = mv_y(B);
-  const int d = abs(ax - bxv) + abs(ay - byv);
-  const float SA = (float)(nB * d), SB = (float)(nA * d);
-  const int x = bx * BS, y = by * BS;
+  *out = A0;
+  if (n == 1) return true;  // all candidates identical: index 0 wins
+  const int x = bx * bs, y = by * bs;
   const int w = a.i1.w, h = a.i1.h, pitch = a.i1.pitch;
   const uint8_t* blk = a.i1.p + (size_t)pair * a.i1.plane + (size_t)y * pitch + x;
   const uint8_t* ref = a.i2.p + (size_t)pair * a.i2.plane;
-  uint32_t Ab[BS == 2 ? 1 : 4];
-  if (BS == 2) {
-    Ab[0] = (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(blk)) | ((uint32_t)__ldg(reinterpret_cast<const uint16_t*>(blk + pitch)) << 16);
-  } else {
-#pragma unroll
-    for (int r = 0; r < (BS == 2 ? 1 : 4); ++r) Ab[r] = __ldg(reinterpret_cast<const uint32_t*>(blk + (size_t)r * pitch));
+  if (more) {
+    if (!any_count) return false;
+    // Four or more distinct vectors (rare outside the first sweep of a level): the same computation with the distinct vectors in
+    // a per-thread column of shared memory (s_u[j * blockDim.x]) and their multiplicities packed four bits each.
+    unsigned long long M = 1ull;
+    int nd = 1;
+    s_u[0] = A0;
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+      if (!has[i]) continue;
+      const uint32_t v = pkin[i];
+      int j = 0;
+      while (j < nd && s_u[j * blockDim.x] != v) ++j;
+      if (j == nd) { s_u[nd * blockDim.x] = v; ++nd; }
+      M += 1ull << (4 * j);
+    }
+    float best = FLT_MAX;
+    uint32_t r = A0;
+#pragma unroll 1
+    for (int j = 0; j < nd; ++j) {
+      const uint32_t uj = s_u[j * blockDim.x];
+      const int xj = mv_x(uj), yj = mv_y(uj);
+      int S = 0;
+      for (int k = 0; k < nd; ++k) {
+        const uint32_t uk = s_u[k * blockDim.x];
+        S += (int)((M >> (4 * k)) & 15ull) * (abs(xj - mv_x(uk)) + abs(yj - mv_y(uk)));
+      }
+      float E = FLT_MAX;
+      if ((unsigned)(x + xj) <= (unsigned)(w - bs) && (unsigned)(y + yj) <= (unsigned)(h - bs))  // :578
+        E = __fadd_rn(__uint2float_rn(block_sad_thread<BSK>(blk, ref + (size_t)(y + yj) * pitch + (x + xj), pitch, bs)),
+                      __fmul_rn(a.lm, (float)S));
+      if (j == 0 || E < best) { best = E; r = uj; }  // first appearance order, strict '<' (:653-659)
+    }
+    *out = r;
+    return true;
   }
-  const int pax = x + ax, pay = y + ay, pbx = x + bxv, pby = y + byv;
-  const bool inA = (unsigned)pax <= (unsigned)(w - BS) && (unsigned)pay <= (unsigned)(h - BS);  // :578
-  const bool inB = (unsigned)pbx <= (unsigned)(w - BS) && (unsigned)pby <= (unsigned)(h - BS);
-  // out-of-image candidates read the block's own position (a valid address) and get FLT_MAX
-  const uint32_t sadA = sad_small<BS>(Ab, ref + (size_t)(inA ? pay : y) * pitch + (inA ? pax : x), pitch);
-  const uint32_t sadB = sad_small<BS>(Ab, ref + (size_t)(inB ? pby : y) * pitch + (inB ? pbx : x), pitch);
-  const float EA = inA ? __fadd_rn(__uint2float_rn(sadA), __fmul_rn(a.lm, SA)) : FLT_MAX;
-  const float EB = inB ? __fadd_rn(__uint2float_rn(sadB), __fmul_rn(a.lm, SB)) : FLT_MAX;
-  *out = (EB < EA) ? B : A0;
+  const int x0 = mv_x(A0), y0 = mv_y(A0), x1 = mv_x(u1), y1 = mv_y(u1), x2 = mv_x(u2), y2 = mv_y(u2);
+  const int d01 = abs(x0 - x1) + abs(y0 - y1), d02 = abs(x0 - x2) + abs(y0 - y2), d12 = abs(x1 - x2) + abs(y1 - y2);
+  const float S0 = (float)(m1 * d01 + m2 * d02), S1 = (float)(m0 * d01 + m2 * d12), S2 = (float)(m0 * d02 + m1 * d12);
+  const bool in0 = (unsigned)(x + x0) <= (unsigned)(w - bs) && (unsigned)(y + y0) <= (unsigned)(h - bs);  // :578
+  const bool in1 = (unsigned)(x + x1) <= (unsigned)(w - bs) && (unsigned)(y + y1) <= (unsigned)(h - bs);
+  const bool in2 = n == 3 && (unsigned)(x + x2) <= (unsigned)(w - bs) && (unsigned)(y + y2) <= (unsigned)(h - bs);
+  float E0 = FLT_MAX, E1 = FLT_MAX, E2 = FLT_MAX;
+  if (BSK <= 4) {
+    // tiny windows: branch-free, out-of-image candidates read the block's own position
+    const uint32_t sad0 = block_sad_thread<BSK>(blk, ref + (size_t)(in0 ? y + y0 : y) * pitch + (in0 ? x + x0 : x), pitch, bs);
+    const uint32_t sad1 = block_sad_thread<BSK>(blk, ref + (size_t)(in1 ? y + y1 : y) * pitch + (in1 ? x + x1 : x), pitch, bs);
+    E0 = in0 ? __fadd_rn(__uint2float_rn(sad0), __fmul_rn(a.lm, S0)) : FLT_MAX;
+    E1 = in1 ? __fadd_rn(__uint2float_rn(sad1), __fmul_rn(a.lm, S1)) : FLT_MAX;
+    if (n == 3) {
+      const uint32_t sad2 = block_sad_thread<BSK>(blk, ref + (size_t)(in2 ? y + y2 : y) * pitch + (in2 ? x + x2 : x), pitch, bs);
+      E2 = in2 ? __fadd_rn(__uint2float_rn(sad2), __fmul_rn(a.lm, S2)) : FLT_MAX;
+    }
+  } else {
+    if (in0) E0 = __fadd_rn(__uint2float_rn(block_sad_thread<BSK>(blk, ref + (size_t)(y + y0) * pitch + (x + x0), pitch, bs)), __fmul_rn(a.lm, S0));
+    if (in1) E1 = __fadd_rn(__uint2float_rn(block_sad_thread<BSK>(blk, ref + (size_t)(y + y1) * pitch + (x + x1), pitch, bs)), __fmul_rn(a.lm, S1));
+    if (in2) E2 = __fadd_rn(__uint2float_rn(block_sad_thread<BSK>(blk, ref + (size_t)(y + y2) * pitch + (x + x2), pitch, bs)), __fmul_rn(a.lm, S2));
+  }
+  uint32_t r = A0;
+  float best = E0;
+  if (E1 < best) { best = E1; r = u1; }
+  if (n == 3 && E2 < best) r = u2;
+  *out = r;
   return true;
 }
 
@@ -1520,6 +1627,10 @@ __device__ __forceinline__ uint32_t reg_eval_team_lean(const RegArgs& a, int pai
 // reached whatever the interleaving), which shortens the tail because the list is in raster order.
 namespace cg = cooperative_groups;
 
+#ifndef BBME_LEVEL_THREADS
+#define BBME_LEVEL_THREADS 512  // threads per CTA of the level kernel (one CTA per SM); 1024 (64 registers) measured slower: spills
+#endif
+
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -1635,19 +1746,19 @@ __device__ __forceinline__ void level_classify(const RegArgs& a, int pair, const
   }
 }
 
-// One sweep at the current block size: classify, then rounds until the work list is empty.
-// BSK: 2 / 4 = one thread per block (two-vector fast path, the rest deferred to the nine-slot evaluator in a second pass of
-// the same round), 8 / 16 / 32 = lean team evaluator (16 / 16 / 32 lanes per block).
+// One sweep at the current block size: classify, then rounds until the work list is empty.  Every listed block is evaluated
+// by one thread (reg_eval_thread).  In a large round (the sweep's first pass) the few blocks with four or more distinct candidate
+// vectors are deferred to a second pass of the same round, so that the warps of the first pass stay converged on the register-only
+// path; a small round (the fix-up tail, where a thread has at most a couple of blocks) evaluates them in line and saves the barrier.
 template <int BSK, bool MULTI>
 __device__ __forceinline__ void level_sweep(const RegArgs& a, int pair, const LevelCtx& lc, uint32_t& ep, uint32_t& rounds,
-                                            uint32_t& blocks) {
-  constexpr int TEAMSZ = BSK <= 4 ? 1 : (BSK >= 32 ? 32 : 16);
+                                            uint32_t& blocks, uint32_t* s_u) {
   const short2* O = a.O + (size_t)pair * a.mv_plane;
   short2* Y = a.Y + (size_t)pair * a.mv_plane;
   uint32_t* Yu = reinterpret_cast<uint32_t*>(Y);
   uint32_t* stamp = a.stamp + (size_t)pair * a.wl_plane;
   uint32_t* lists[2] = {a.list0 + (size_t)pair * a.wl_plane, a.list1 + (size_t)pair * a.wl_plane};
-  uint32_t* dlist = reinterpret_cast<uint32_t*>(a.nv) + (size_t)pair * a.wl_plane;  // blocks deferred to the nine-slot evaluator
+  uint32_t* dlist = reinterpret_cast<uint32_t*>(a.nv) + (size_t)pair * a.wl_plane;  // blocks deferred to the second pass
   const int lane = threadIdx.x & 31;
   if (lc.gtid == 0) {
 #pragma unroll
@@ -1662,7 +1773,6 @@ __device__ __forceinline__ void level_sweep(const RegArgs& a, int pair, const Le
   level_classify(a, pair, lc, lists[0]);
   level_sync<MULTI>();
   if (prof) { const unsigned long long t1 = globaltimer_ns(); prof[0] += (uint32_t)(t1 - t0); t0 = t1; prof[4] += lc.cnt[0]; }
-  const uint32_t tl = lc.gtid % TEAMSZ;
   for (int r = 0;; ++r) {
     // round r reads list[r & 1] (counter r % 3), appends to list[(r + 1) & 1] (counter (r + 1) % 3) and clears counter
     // (r + 2) % 3, which was last read before the barrier that precedes this round; the deferred list's counter alternates
@@ -1677,82 +1787,87 @@ __device__ __forceinline__ void level_sweep(const RegArgs& a, int pair, const Le
     uint32_t* lnext = lists[(r + 1) & 1];
     uint32_t* next_count = &lc.cnt[(r + 1) % 3];
     uint32_t* dcount = &lc.cnt[3 + (r & 1)];
+    const bool in_line = cnt <= 2u * lc.gthreads;  // the same for every thread of the cluster
     ++ep;
-    if (BSK <= 4) {
-      // One thread per block, software-pipelined: the list entry is loaded two iterations ahead and the nine vectors one
-      // iteration ahead, so that an evaluation waits for ONE memory round trip (its windows) instead of three dependent
-      // ones.  Reading the vectors early is safe: a block that read a neighbour's old value is re-enqueued by that
-      // neighbour's push, whenever the read happened (chaotic iteration).
-      const uint32_t limit = (cnt + 31u) / 32u * 32u;  // whole warps iterate together
-      uint32_t e = lc.gtid;
-      int b1 = e < limit ? (int)lcur[e < cnt ? e : cnt - 1] : 0;
-      int b2 = e + lc.gthreads < limit ? (int)lcur[e + lc.gthreads < cnt ? e + lc.gthreads : cnt - 1] : 0;
+    if (BSK >= 8 && in_line) {
+      // A small round of large blocks is a latency problem, not a throughput problem: a team of lanes per block (one window
+      // row per lane, all distinct candidates in one or two round trips) instead of one thread walking through 16 rows of
+      // every candidate.
+      constexpr int TEAMSZ = BSK >= 32 ? 32 : 16;
+      constexpr int TPW = 32 / TEAMSZ;
+      const uint32_t team = lc.gtid / TEAMSZ, tl = lc.gtid % TEAMSZ, nteams = lc.gthreads / TEAMSZ;
+      const uint32_t limit = (cnt + TPW - 1) / TPW * TPW;
+      for (uint32_t e = team; e < limit; e += nteams) {
+        const bool live = e < cnt;
+        const int b = (int)lcur[live ? e : cnt - 1];
+        const int bx = b % a.gw, by = b / a.gw;
+        bool valid = false;
+        const uint32_t my = team_slot_load(a, O, Y, bx, by, (int)tl, valid);
+        const uint32_t nv = reg_eval_team_lean<BSK <= 4 ? 8 : BSK>(a, pair, bx, by, (int)tl, live, my, valid);
+        const bool changed = tl == 0 && live && nv != Yu[b];
+        if (changed) Yu[b] = nv;
+        push_dependents(changed, bx, by, a.gw, a.gh, stamp, ep, lnext, next_count);
+      }
+    } else {
+      // Software-pipelined: the list entry is loaded two iterations ahead and the nine vectors one iteration ahead, so that an
+      // evaluation waits for ONE memory round trip (its windows) instead of three dependent ones.  Reading the vectors early
+      // is safe: a block that read a neighbour's old value is re-enqueued by that neighbour's push, whenever the read happened
+      // (chaotic iteration).
+      // (Tried: a thread taking runs of four consecutive list entries and patching the next entry's "L" vector with the value
+      // just computed -- an in-place sweep along the row inside a run.  It saves a quarter of the later rounds' blocks but
+      // not one round, and the strided list reads cost more than that: K = 1.)
+      constexpr uint32_t K = 1u;
+      const uint32_t runs = (cnt + K - 1u) / K;
+      const uint32_t run_limit = (runs + 31u) / 32u * 32u;  // whole warps iterate together
+      const uint32_t G = lc.gthreads;
+      uint32_t run = lc.gtid, k = 0;
+      auto advance = [&](uint32_t& rr, uint32_t& kk) { if (++kk == K) { kk = 0; rr += G; } };
+      auto load_entry = [&](uint32_t rr, uint32_t kk) -> int {
+        const uint32_t e = rr * K + kk;
+        return rr < run_limit ? (int)lcur[e < cnt ? e : cnt - 1] : 0;
+      };
+      uint32_t r1 = run, k1 = k;   // position of b1
+      uint32_t r2 = run, k2 = k;   // position of b2
+      advance(r2, k2);
+      int b1 = load_entry(r1, k1);
+      int b2 = load_entry(r2, k2);
       uint32_t A1 = 0, pk1[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) pk1[i] = 0;
-      if (e < limit) small_gather(a, O, Y, b1 % a.gw, b1 / a.gw, A1, pk1);
-      for (; e < limit; e += lc.gthreads) {
-        const bool live = e < cnt;
+      if (r1 < run_limit) small_gather(a, O, Y, b1 % a.gw, b1 / a.gw, A1, pk1);
+      while (r1 < run_limit) {
+        const bool live = r1 * K + k1 < cnt;
         const int b = b1;
         const uint32_t A0 = A1;
         uint32_t pk[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) pk[i] = pk1[i];
-        b1 = b2;
-        const uint32_t e2 = e + 2 * lc.gthreads;
-        if (e2 < limit) b2 = (int)lcur[e2 < cnt ? e2 : cnt - 1];
-        if (e + lc.gthreads < limit) small_gather(a, O, Y, b1 % a.gw, b1 / a.gw, A1, pk1);
+        // shift the pipeline: b1 <- b2, b2 <- the entry after it
+        b1 = b2; r1 = r2; k1 = k2;
+        advance(r2, k2);
+        b2 = load_entry(r2, k2);
+        if (r1 < run_limit) small_gather(a, O, Y, b1 % a.gw, b1 / a.gw, A1, pk1);
         const int bx = b % a.gw, by = b / a.gw;
         uint32_t nv = 0;
-        const bool done = !live || reg_eval_small_fast<BSK>(a, pair, bx, by, A0, pk, &nv);
-        const uint32_t dm = __ballot_sync(0xffffffffu, !done);
-        if (dm) {
-          uint32_t dbase = 0;
-          const int leader = __ffs(dm) - 1;
-          if (lane == leader) dbase = atomicAdd(dcount, (uint32_t)__popc(dm));
-          dbase = __shfl_sync(0xffffffffu, dbase, leader);
-          if (!done) dlist[dbase + __popc(dm & ((1u << lane) - 1u))] = (uint32_t)b;
+        const bool done = !live || reg_eval_thread<BSK>(a, pair, bx, by, A0, pk, &nv, in_line, s_u);
+        if (!in_line) {
+          const uint32_t dm = __ballot_sync(0xffffffffu, !done);
+          if (dm) {
+            uint32_t dbase = 0;
+            const int leader = __ffs(dm) - 1;
+            if (lane == leader) dbase = atomicAdd(dcount, (uint32_t)__popc(dm));
+            dbase = __shfl_sync(0xffffffffu, dbase, leader);
+            if (!done) dlist[dbase + __popc(dm & ((1u << lane) - 1u))] = (uint32_t)b;
+          }
         }
         const bool changed = live && done && nv != Yu[b];
         if (changed) Yu[b] = nv;
+        if (live && done && b1 == b + 1 && bx + 1 < a.gw) pk1[0] = nv;  // the next block's left neighbour is this block
         push_dependents(changed, bx, by, a.gw, a.gh, stamp, ep, lnext, next_count);
       }
-    } else {
-      // A team per block.  A warp takes 32 consecutive list entries with one coalesced load; each of its teams walks through
-      // its share in list (= raster) order, loading the next block's nine vectors -- one per lane -- while the current block's
-      // windows are in flight.  The list is in raster order, so the next block is usually the right-hand neighbour: its "L"
-      // vector is patched with the value just computed (an in-place sweep along the row inside a batch, as in the reference).
-      const uint32_t nsb = (cnt + 31u) / 32u;
-      const uint32_t warp_g = lc.gtid >> 5, nwarps = lc.gthreads >> 5;
-      const int base = lane - (int)tl;
-      for (uint32_t sb = warp_g; sb < nsb; sb += nwarps) {
-        const uint32_t e0 = sb * 32u;
-        const uint32_t mine = e0 + (uint32_t)lane;
-        const uint32_t entry = lcur[mine < cnt ? mine : cnt - 1];
-        int bn = (int)__shfl_sync(0xffffffffu, entry, base);
-        bool vn = false;
-        uint32_t myn = team_slot_load(a, O, Y, bn % a.gw, bn / a.gw, (int)tl, vn);
-#pragma unroll 1
-        for (int k = 0; k < TEAMSZ; ++k) {
-          const int b = bn;
-          const uint32_t my = myn;
-          const bool valid = vn;
-          const bool live = e0 + (uint32_t)(base + k) < cnt;
-          if (k + 1 < TEAMSZ) {
-            bn = (int)__shfl_sync(0xffffffffu, entry, base + k + 1);
-            myn = team_slot_load(a, O, Y, bn % a.gw, bn / a.gw, (int)tl, vn);
-          }
-          const int bx = b % a.gw, by = b / a.gw;
-          const uint32_t nv = reg_eval_team_lean<BSK>(a, pair, bx, by, (int)tl, live, my, valid);
-          const bool changed = tl == 0 && live && nv != Yu[b];
-          if (changed) Yu[b] = nv;
-          if (tl == 1 && live && vn && bn == b + 1) myn = nv;  // the next block's left neighbour is this block
-          push_dependents(changed, bx, by, a.gw, a.gh, stamp, ep, lnext, next_count);
-        }
-      }
     }
-    if (BSK <= 4) {
-      // second pass of the round: the blocks with three or more distinct candidate vectors
+    if (!in_line) {
+      // second pass of a large round: the blocks with four or more distinct candidate vectors
       if (MULTI) __threadfence();
       level_sync<MULTI>();
       const uint32_t dcnt = *reinterpret_cast<volatile uint32_t*>(dcount);
@@ -1762,15 +1877,13 @@ __device__ __forceinline__ void level_sweep(const RegArgs& a, int pair, const Le
         const bool live = e < dcnt;
         const int b = (int)dlist[live ? e : dcnt - 1];
         const int bx = b % a.gw, by = b / a.gw;
-        const short2 nv2 = reg_eval_small<BSK == 2 ? 2 : 4>(a, pair, O, Y, bx, by, live);
-        const bool changed = live && pack_mv(nv2) != Yu[b];
-        if (changed) Y[b] = nv2;
+        uint32_t A0, pk[8], nv = 0;
+        small_gather(a, O, Y, bx, by, A0, pk);
+        if (live) reg_eval_thread<BSK>(a, pair, bx, by, A0, pk, &nv, true, s_u);
+        const bool changed = live && nv != Yu[b];
+        if (changed) Yu[b] = nv;
         push_dependents(changed, bx, by, a.gw, a.gh, stamp, ep, lnext, next_count);
       }
-    }
-    if (r > 0) {  // the first pass is the sweep itself; later rounds are the fix-up
-      rounds += 1;
-      blocks += cnt;
     }
     if (MULTI) __threadfence();
     level_sync<MULTI>();
@@ -1780,12 +1893,20 @@ __device__ __forceinline__ void level_sweep(const RegArgs& a, int pair, const Le
       t0 = t1;
       if (r > 0) { prof[3] += 1; prof[5] += cnt; }
     }
+    if (r > 0) {  // the first pass is the sweep itself; later rounds are the fix-up
+      rounds += 1;
+      blocks += cnt;
+    }
   }
 }
 
+constexpr int kLevelThreads = BBME_LEVEL_THREADS;
+
 template <bool MULTI>
-__global__ void __launch_bounds__(512, 1) k_reg_level(RegArgs a, int sweeps, float lambda0, int first_mult, int single_stage) {
+__global__ void __launch_bounds__(kLevelThreads, 1) k_reg_level(RegArgs a, int sweeps, float lambda0, int first_mult, int single_stage) {
   __shared__ uint32_t s_cnt[8];
+  __shared__ uint32_t s_ucol[9 * kLevelThreads];  // per-thread columns of distinct candidate vectors (reg_eval_thread)
+  uint32_t* s_u = s_ucol + threadIdx.x;
   LevelCtx lc;
   int pair;
   if (MULTI) {
@@ -1817,11 +1938,11 @@ __global__ void __launch_bounds__(512, 1) k_reg_level(RegArgs a, int sweeps, flo
     for (int sw = first_mult; sw < first_mult + sweeps; ++sw) {
       a.lm = lambda * (float)sw;  // lambda * (float)lambda_multiplier, motion_framework.cpp:607
       switch (g >= 32 ? 32 : g) {
-        case 32: level_sweep<32, MULTI>(a, pair, lc, ep, rounds, blocks); break;
-        case 16: level_sweep<16, MULTI>(a, pair, lc, ep, rounds, blocks); break;
-        case 8: level_sweep<8, MULTI>(a, pair, lc, ep, rounds, blocks); break;
-        case 4: level_sweep<4, MULTI>(a, pair, lc, ep, rounds, blocks); break;
-        default: level_sweep<2, MULTI>(a, pair, lc, ep, rounds, blocks); break;
+        case 32: level_sweep<32, MULTI>(a, pair, lc, ep, rounds, blocks, s_u); break;
+        case 16: level_sweep<16, MULTI>(a, pair, lc, ep, rounds, blocks, s_u); break;
+        case 8: level_sweep<8, MULTI>(a, pair, lc, ep, rounds, blocks, s_u); break;
+        case 4: level_sweep<4, MULTI>(a, pair, lc, ep, rounds, blocks, s_u); break;
+        default: level_sweep<2, MULTI>(a, pair, lc, ep, rounds, blocks, s_u); break;
       }
       const short2* t = a.O; a.O = a.Y; a.Y = const_cast<short2*>(t);
     }
@@ -1866,18 +1987,19 @@ __global__ void __launch_bounds__(512, 1) k_reg_level(RegArgs a, int sweeps, flo
   if (MULTI) level_sync<MULTI>();
 }
 
-int launch_reg_level(const RegArgs& a, int sweeps, float lambda0, int first_mult, int single_stage, int n, int sm_count,
+int launch_reg_level(const RegArgs& a, int sweeps, float lambda0, int first_mult, int single_stage, int n, int sm_budget,
                      cudaStream_t s) {
-  // cluster size: spread a pair over several SMs while the chunk leaves SMs idle
+  // cluster size: spread a pair over several SMs while the chunk leaves SMs of its budget idle (the budget is the GPU divided by
+  // the pipeline slots: chunks of other slots run beside this one)
   int cs = 1;
-  while (cs < 8 && 2 * cs * n <= sm_count) cs *= 2;
+  while (cs < 8 && 2 * cs * n <= sm_budget) cs *= 2;
   if (const char* e = getenv("BBME_REG_CLUSTER")) {
     const int v = atoi(e);
     if (v == 1 || v == 2 || v == 4 || v == 8) cs = v;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(n * cs));
-  cfg.blockDim = dim3(512);
+  cfg.blockDim = dim3(kLevelThreads);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -1889,7 +2011,7 @@ int launch_reg_level(const RegArgs& a, int sweeps, float lambda0, int first_mult
   cfg.numAttrs = 1;
   cudaError_t e;
   if (cs == 1) {
-    k_reg_level<false><<<n, 512, 0, s>>>(a, sweeps, lambda0, first_mult, single_stage);
+    k_reg_level<false><<<n, kLevelThreads, 0, s>>>(a, sweeps, lambda0, first_mult, single_stage);
     e = cudaGetLastError();
   } else {
     e = cudaLaunchKernelEx(&cfg, k_reg_level<true>, a, sweeps, lambda0, first_mult, single_stage);

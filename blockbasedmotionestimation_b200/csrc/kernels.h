@@ -77,7 +77,7 @@ void launch_reg_fix(const RegArgs& a, int r0, int n, cudaStream_t s);
 // after the search; the result ends in a.O or a.Y depending on the number of sweeps and splits (the caller tracks the
 // ping-pong like the per-sweep path does).  Returns 0 or -1 (launch failure).
 // first_mult: lambda_multiplier of the first sweep (1 in the schedule); single_stage: stop after the sweeps of a.bs.
-int launch_reg_level(const RegArgs& a, int sweeps, float lambda0, int first_mult, int single_stage, int n, int sm_count,
+int launch_reg_level(const RegArgs& a, int sweeps, float lambda0, int first_mult, int single_stage, int n, int sm_budget,
                      cudaStream_t s);
 
 // VABSDIFF4 issue-rate micro-benchmark (kernels.cu); returns 0 on success
