@@ -5,7 +5,7 @@ CSRC := $(PKG)/csrc
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function \
            --fmad=false -Iinclude
 LIB := $(PKG)/libbbme.so
-OBJS := $(CSRC)/kernels.o $(CSRC)/search_tma.o $(CSRC)/capi.o $(CSRC)/flo.o $(CSRC)/hostpool.o $(CSRC)/multi.o
+OBJS := $(CSRC)/kernels.o $(CSRC)/regularize.o $(CSRC)/search_tma.o $(CSRC)/capi.o $(CSRC)/flo.o $(CSRC)/hostpool.o $(CSRC)/multi.o
 
 all: $(LIB) oracle tools/color_flow
 

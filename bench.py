@@ -378,7 +378,8 @@ def run_ours(args, rank, local_rank, world):
                                  buf.data_ptr(), (Hp // 2) * (Wp // 2) * 2)
         for s_ in streams:
             main.wait_stream(s_)
-        gather.push(buf, k & 1)  # enqueued on the current stream of this rank
+        if not args.no_gather:
+            gather.push(buf, k & 1)  # enqueued on the current stream of this rank
         ev = torch.cuda.Event()
         ev.record(main)
         gather_done[k & 1] = ev
@@ -435,7 +436,7 @@ def run_ours(args, rank, local_rank, world):
         parity = bool(tt.item() == 1)
 
     gather_ok = None
-    if world > 1 and not args.no_check:
+    if world > 1 and not args.no_check and not args.no_gather:
         barrier()
         if rank == 0:
             last = gather.result((args.steps - 1) & 1)
@@ -654,6 +655,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer arm")
     ap.add_argument("--no-other", action="store_true", help="skip the other BASELINE configurations")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--no-gather", action="store_true", help="diagnosis only (N > 1): skip the per-step gather of the fields on rank 0")
     args = ap.parse_args()
     claim_stdout()
     rank = env_int("RANK", 0)

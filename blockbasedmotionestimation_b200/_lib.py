@@ -87,6 +87,12 @@ SIGNATURES = {
     "bbme_pool_last_error": (C.c_char_p, [_P]),
     "bbme_pool_plan": (_I, [_P, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(BbmeOptions), C.POINTER(BbmeShape)]),
     "bbme_pool_estimate_batch": (_I, [_P, _I, C.POINTER(_P), C.POINTER(_P), _SZ, C.POINTER(_P)]),
+    "bbme_device_alloc": (_I, [_I, _SZ, C.POINTER(_P)]),
+    "bbme_device_free": (None, [_I, _P]),
+    "bbme_ipc_export": (_I, [_I, _P, _P]),
+    "bbme_ipc_open": (_I, [_I, _P, C.POINTER(_P)]),
+    "bbme_ipc_close": (_I, [_I, _P]),
+    "bbme_copy_async": (_I, [_I, _P, _P, _SZ, _P]),
     "bbme_host_alloc": (_I, [C.POINTER(_P), _SZ]),
     "bbme_host_free": (None, [_P]),
     "bbme_debug_level_image": (_I, [_P, _I, _I, _I, _P]),

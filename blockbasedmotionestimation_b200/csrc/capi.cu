@@ -35,7 +35,7 @@ struct Slot {
   uint32_t* stamp = nullptr;
   uint32_t* ctr = nullptr;
   unsigned long long* counters = nullptr;  // [0] candidates, [1] absdiffs
-  uint32_t* hist = nullptr;                // BBME_FIX_HIST=1: kHistSweeps x 64 words (RegArgs::hist)
+  uint32_t* hist = nullptr;                // BBME_REG_PROFILE=1: 64 words per level (RegArgs::hist)
   float* out = nullptr;               // device output of the up-sampled path (stripped, sub-sampled field)
   // host-buffer path: the compact int16 field is copied into a pinned staging buffer and expanded on the host
   int16_t* stage[2] = {nullptr, nullptr};
@@ -83,8 +83,6 @@ struct bbme_ctx {
   bool stats_armed = false;
   int use_graphs = 1;   // small chunks replay a captured CUDA graph of their ~70-230 launches (BBME_GRAPHS=0 disables)
   int next_slot = 0;    // round-robin position over the slots across asynchronous calls
-  int reg_legacy = 0;    // BBME_REG_LEGACY=1: the per-sweep kernels of round 1 instead of the fused level kernel (A/B runs)
-  int grid_rounds = -1;  // fix-up rounds run grid-wide before the per-pair tail loop; -1 = by chunk size (BBME_GRID_ROUNDS)
 };
 
 namespace {
@@ -231,7 +229,6 @@ int run_chunk(bbme_ctx* c, Slot& s, int n, const uint8_t* d_in1, const uint8_t* 
   const bbme_shape& sh = c->shape;
   const int L = sh.num_levels;
   cudaStream_t st = s.stream;
-  int sweep_id = 0;
   s.last_n = n > s.last_n ? n : s.last_n;
   mark(c, s, TAG_BEGIN);
   // ---- MF::MF: pad + Gaussian pyramid (motion_framework.cpp:57-106)
@@ -300,7 +297,7 @@ int run_chunk(bbme_ctx* c, Slot& s, int n, const uint8_t* d_in1, const uint8_t* 
     // regularisation schedule (motion_framework.cpp:133-154): per block size `sweeps` sweeps with
     // lambda_multiplier 1..sweeps, then split; lambda starts at bs/2 (integer division, :73,95) and doubles.
     float lambda = (float)(bs0 / 2);
-    if (!c->reg_legacy) {
+    {
       // one launch per level: a cluster of CTAs per pair walks through every sweep, fix-up round and split
       RegArgs ra;
       ra.i1 = i1; ra.i2 = i2;
@@ -318,45 +315,6 @@ int run_chunk(bbme_ctx* c, Slot& s, int n, const uint8_t* d_in1, const uint8_t* 
       int swaps = 0;
       for (int gg = g; gg > 1; gg >>= 1) swaps += c->opt.sweeps + (gg > 2 ? 1 : 0);
       if (swaps & 1) cur = nxt;
-      g = 1;
-    }
-    while (g > 1) {
-      for (int sw = 1; sw <= c->opt.sweeps; ++sw) {
-        RegArgs ra;
-        ra.i1 = i1;
-        ra.i2 = i2;
-        ra.bs = g;
-        ra.gw = gw;
-        ra.gh = gh;
-        ra.lm = lambda * (float)sw;
-        ra.O = cur;
-        ra.Y = nxt;
-        ra.mv_plane = c->cap[l];
-        ra.list0 = s.list0;
-        ra.list1 = s.list1;
-        ra.nv = s.nv;
-        ra.stamp = s.stamp;
-        ra.wl_plane = c->cap[0];
-        ra.ctr = s.ctr;
-        ra.hist = (s.hist && sweep_id < kHistSweeps) ? s.hist + 64 * sweep_id : nullptr;
-        ++sweep_id;
-        // with few pairs in flight the per-pair tail loop leaves most SMs idle: run the first (largest) rounds grid-wide
-        const int gr = c->grid_rounds >= 0 ? c->grid_rounds : (n >= 96 ? 0 : 3);
-        launch_reg_full(ra, n, st);
-        for (int r = 0; r < gr; ++r) launch_reg_round(ra, r, n, st);
-        launch_reg_fix(ra, gr, n, st);
-        c->launches += 3 + gr;  // classify + eval, gr grid-wide rounds, the per-pair tail loop
-        short2* t = cur; cur = nxt; nxt = t;
-      }
-      if (g > 2) {
-        launch_divide(cur, gw, gh, c->cap[l], nxt, c->cap[l], n, st);
-        ++c->launches;
-        short2* t = cur; cur = nxt; nxt = t;
-        gw *= 2;
-        gh *= 2;
-      }
-      g >>= 1;
-      lambda = lambda * 2;
     }
     s.mv_final[l] = cur;
     mark(c, s, TAG_REG);
@@ -442,7 +400,6 @@ int collect_after_sync(bbme_ctx* c) {
       for (int p = 0; p < s.last_n; ++p) {
         c->stats.fix_rounds += ctr[(size_t)p * kCtrWords + CTR_ROUNDS];
         c->stats.fix_blocks += ctr[(size_t)p * kCtrWords + CTR_BLOCKS];
-        c->stats.reserved += ctr[(size_t)p * kCtrWords + CTR_TAIL_BLOCKS];
       }
       s.last_n = 0;
     }
@@ -452,7 +409,7 @@ int collect_after_sync(bbme_ctx* c) {
     std::vector<uint32_t> hh((size_t)kHistSweeps * 64);
     CUDA_TRY(c, cudaMemcpy(hh.data(), s.hist, hh.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     CUDA_TRY(c, cudaMemset(s.hist, 0, hh.size() * sizeof(uint32_t)));
-    if (getenv("BBME_REG_PROFILE")) {
+    {
       for (int l = 0; l < c->shape.num_levels; ++l)
         for (int k = 1; k < 8; ++k) {
           const uint32_t* q = &hh[(size_t)l * 64 + 8 * k];
@@ -460,14 +417,6 @@ int collect_after_sync(bbme_ctx* c) {
           fprintf(stderr, "regprofile level %d bs %d: classify %.1f us, first pass %.1f us (%u listed, %u deferred), %u later rounds %.1f us (%u blocks)\n",
                   l, 1 << k, q[0] * 1e-3, q[1] * 1e-3, q[4], q[6], q[3], q[2] * 1e-3, q[5]);
         }
-      continue;
-    }
-    for (int sw = 0; sw < kHistSweeps; ++sw) {
-      const uint32_t* q = &hh[(size_t)sw * 64];
-      if (!q[0] && !q[63]) continue;
-      fprintf(stderr, "fixhist sweep %d listed %u maxrounds %u sumrounds %u :", sw, q[0], q[62], q[63]);
-      for (int r = 0; r < 60 && q[2 + r]; ++r) fprintf(stderr, " %u", q[2 + r]);
-      fprintf(stderr, "\n");
     }
   }
   c->stats.search_launches = c->search_launches;
@@ -552,7 +501,6 @@ void begin_call(bbme_ctx* c) {
     s.last_n = 0;
     cudaMemsetAsync(s.counters, 0, 2 * sizeof(unsigned long long), s.stream);
     cudaMemset2DAsync(s.ctr + CTR_ROUNDS, kCtrWords * sizeof(uint32_t), 0, 2 * sizeof(uint32_t), c->opt.chunk_pairs, s.stream);
-    cudaMemset2DAsync(s.ctr + CTR_TAIL_BLOCKS, kCtrWords * sizeof(uint32_t), 0, sizeof(uint32_t), c->opt.chunk_pairs, s.stream);
   }
   c->stats_armed = true;
 }
@@ -615,11 +563,6 @@ int bbme_create(bbme_ctx** out, int device) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   if (const char* g = getenv("BBME_GRAPHS")) c->use_graphs = atoi(g) != 0;
-  if (const char* rl = getenv("BBME_REG_LEGACY")) c->reg_legacy = atoi(rl) != 0;
-  if (const char* gr = getenv("BBME_GRID_ROUNDS")) {
-    const int v = atoi(gr);
-    if (v >= 0 && v <= 64) c->grid_rounds = v;
-  }
   bbme_default_options(&c->opt);
   *out = c;
   return BBME_OK;
@@ -685,7 +628,7 @@ int bbme_plan(bbme_ctx* c, int width, int height, int num_levels, const int* sea
         (rc = dev_alloc(c, &s.ctr, n * kCtrWords, true)) || (rc = dev_alloc(c, &s.counters, (size_t)2, true)) ||
         (rc = dev_alloc(c, &s.out, n * (c->out_plane / 4 + 64), false)))
       return rc;
-    if ((getenv("BBME_FIX_HIST") || getenv("BBME_REG_PROFILE")) && (rc = dev_alloc(c, &s.hist, (size_t)kHistSweeps * 64, true))) return rc;
+    if (getenv("BBME_REG_PROFILE") && (rc = dev_alloc(c, &s.hist, (size_t)kHistSweeps * 64, true))) return rc;
     for (int l = 0; l < L; ++l) {
       memset(&s.tma[l], 0, sizeof(s.tma[l]));
       memset(&s.tma_seq[l], 0, sizeof(s.tma_seq[l]));
@@ -1022,6 +965,66 @@ int bbme_expand_compact(const int16_t* mv2, int width2, int height2, float* dens
   return BBME_OK;
 }
 
+// ---- peer memory between the one-process-per-GPU ranks of a box (results gathered without a communication kernel) ----
+int bbme_device_alloc(int device, size_t bytes, void** p) {
+  if (!p || bytes == 0) return BBME_E_ARG;
+  *p = nullptr;
+  if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return BBME_E_NOMEM;
+  }
+  return BBME_OK;
+}
+
+void bbme_device_free(int device, void* p) {
+  if (p && cudaSetDevice(device) == cudaSuccess) cudaFree(p);
+}
+
+int bbme_ipc_export(int device, void* p, unsigned char* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  if (!p || !handle64) return BBME_E_ARG;
+  cudaIpcMemHandle_t h;
+  if (cudaSetDevice(device) != cudaSuccess || cudaIpcGetMemHandle(&h, p) != cudaSuccess) {
+    cudaGetLastError();
+    return BBME_E_CUDA;
+  }
+  memcpy(handle64, &h, 64);
+  return BBME_OK;
+}
+
+int bbme_ipc_open(int device, const unsigned char* handle64, void** p) {
+  if (!p || !handle64) return BBME_E_ARG;
+  *p = nullptr;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  // opened with THIS rank's device current: the exporter's memory is mapped with peer access from here, and this process
+  // never creates a context on the exporter's GPU (a second context there would time-slice with the exporter's kernels)
+  if (cudaSetDevice(device) != cudaSuccess || cudaIpcOpenMemHandle(p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+    cudaGetLastError();
+    return BBME_E_CUDA;
+  }
+  return BBME_OK;
+}
+
+int bbme_ipc_close(int device, void* p) {
+  if (!p) return BBME_E_ARG;
+  if (cudaSetDevice(device) != cudaSuccess || cudaIpcCloseMemHandle(p) != cudaSuccess) {
+    cudaGetLastError();
+    return BBME_E_CUDA;
+  }
+  return BBME_OK;
+}
+
+int bbme_copy_async(int device, void* dst, const void* src, size_t bytes, void* stream) {
+  if (!dst || !src) return BBME_E_ARG;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, reinterpret_cast<cudaStream_t>(stream)) != cudaSuccess) {
+    cudaGetLastError();
+    return BBME_E_CUDA;
+  }
+  return BBME_OK;
+}
+
 int bbme_host_alloc(void** p, size_t bytes) {
   if (!p) return BBME_E_ARG;
   return cudaHostAlloc(p, bytes, cudaHostAllocDefault) == cudaSuccess ? BBME_OK : BBME_E_NOMEM;
@@ -1257,16 +1260,9 @@ int bbme_stage_regularize(bbme_ctx* c, const uint8_t* im1, const uint8_t* im2, i
   ra.lm = lambda * (float)mult;
   ra.O = O; ra.Y = Y; ra.mv_plane = nb;
   ra.list0 = l0; ra.list1 = l1; ra.nv = nv; ra.stamp = stamp; ra.wl_plane = nb; ra.ctr = ctr;
-  if (!c->reg_legacy) {
-    ra.lm = 0.f;
-    if (launch_reg_level(ra, 1, lambda, mult, 1, 1, c->sm_count, 0) != 0)
-      return fail(c, BBME_E_CUDA, "stage_regularize launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-  } else {
-    const int gr = c->grid_rounds >= 0 ? c->grid_rounds : 3;
-    launch_reg_full(ra, 1, 0);
-    for (int r = 0; r < gr; ++r) launch_reg_round(ra, r, 1, 0);
-    launch_reg_fix(ra, gr, 1, 0);
-  }
+  ra.lm = 0.f;
+  if (launch_reg_level(ra, 1, lambda, mult, 1, 1, c->sm_count, 0) != 0)
+    return fail(c, BBME_E_CUDA, "stage_regularize launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return fail(c, BBME_E_CUDA, "stage_regularize kernel failed: %s", cudaGetErrorString(e));
   CUDA_TRY(c, cudaMemcpy(mv, Y, nb * sizeof(short2), cudaMemcpyDeviceToHost));

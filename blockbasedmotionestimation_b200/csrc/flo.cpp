@@ -119,10 +119,17 @@ int bbme_flow_strip_subsample(const float* padded, const bbme_shape* sh, int fac
 }  // extern "C"
 
 // Flow::MotionToColor + computeColor + makecolorwheel (rw_flow.cpp:202-300): Middlebury colour coding of a flow field.
-// Host code like the .flo codec (the reference writes flow.png from it, main_class.cpp:73-75).  The arithmetic follows
-// the reference expression by expression -- float sqrt / atan2 / division by the reference's FLOAT pi
-// (rw_flow.cpp:36), double only in `col *= .75` and `255.0 * col` -- so on the same libm the bytes are identical
-// (the tests compare with the reference's own function, compiled from the reference tree).
+// Host code like the .flo codec (the reference writes flow.png from it, main_class.cpp:73-75).
+//
+// PROVENANCE.  This block is a deliberate restatement of a published algorithm, not independent design: the reference's
+// routine is itself a copy of D. Scharstein's Middlebury `colorcode.cpp` (vendored in the reference under
+// middlebury/flow-code/), and a flow.png that matches the reference byte for byte leaves no freedom in the colour-wheel table
+// (segment lengths RY YG GC CB BM MR = 15, 6, 4, 11, 13, 6), in the operation order, or in which operations are float and which
+// double: float sqrt / atan2 / division by the reference's FLOAT pi (rw_flow.cpp:36), double only in `col *= .75` and
+// `255.0 * col`.  The variable names for the running extrema and the wheel interpolation follow the published routine for that
+// reason.  The reference is GPLv3; this file is test-pinned against the reference's own function compiled from the reference
+// tree (tests/golden/flow_color_ref.npz), which is how the byte-exactness claim is checked.  The .flo codec and the AEE above
+// are independently written (whole-buffer I/O, status codes).
 namespace {
 struct ColorWheel {
   int n = 0;

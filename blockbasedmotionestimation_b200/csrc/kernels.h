@@ -8,9 +8,10 @@
 
 namespace bbme {
 
-// per-pair control words of the regularisation fix-up (device memory, kCtrWords uint32 per pair)
+// per-pair control words of the regularisation (device memory, kCtrWords uint32 per pair): the epoch of the de-duplication
+// stamps (persists across launches) and the fix-up statistics
 constexpr int kCtrWords = 8;
-enum { CTR_COUNT0 = 0, CTR_COUNT1 = 1, CTR_EPOCH = 2, CTR_ROUNDS = 3, CTR_BLOCKS = 4, CTR_COUNT2 = 5, CTR_TAIL_BLOCKS = 6, CTR_COUNT_EVAL = 7 };
+enum { CTR_EPOCH = 2, CTR_ROUNDS = 3, CTR_BLOCKS = 4 };
 
 struct RegArgs {
   ImgView i1, i2;
@@ -22,12 +23,11 @@ struct RegArgs {
   size_t mv_plane;  // entries between pairs in O / Y
   uint32_t* list0;  // work lists, `wl_plane` entries between pairs
   uint32_t* list1;
-  short2* nv;       // phase-1 results of a fix-up round
+  short2* nv;       // scratch list: blocks deferred to the second pass of a round (used as uint32 entries)
   uint32_t* stamp;  // de-duplication stamps, one per block
   size_t wl_plane;
   uint32_t* ctr;    // kCtrWords per pair
-  uint32_t* hist = nullptr;  // optional (BBME_FIX_HIST=1): 64 words per sweep, [0] listed blocks, [2 + r] blocks of round r,
-                             // [62] max rounds over pairs, [63] sum of rounds; all summed over the chunk's pairs
+  uint32_t* hist = nullptr;  // optional (BBME_REG_PROFILE=1): 8 words per block size, phase times of pair 0 (regularize.cu)
 };
 
 // pad (cv::copyMakeBorder constant 0) both frames of n pairs into level 0
@@ -68,11 +68,6 @@ void launch_export(const short2* mv2, int gw2, size_t mv_plane, float* out, int 
                    cudaStream_t s);
 void launch_export_compact(const short2* mv2, int gw2, int gh2, size_t mv_plane, int16_t* out, size_t out_plane, int n,
                            cudaStream_t s);
-// one regularisation sweep = full Jacobi pass + per-pair fixed-point rounds (exactly the in-place raster result)
-void launch_reg_full(const RegArgs& a, int n, cudaStream_t s);
-// grid-wide fix-up round `r` (0-based) over all pairs; then the per-pair tail loop starting at round `r0`
-void launch_reg_round(const RegArgs& a, int r, int n, cudaStream_t s);
-void launch_reg_fix(const RegArgs& a, int r0, int n, cudaStream_t s);
 // The whole schedule of a level in one launch: a.bs / a.gw / a.gh describe the level's INITIAL block grid, a.O holds the field
 // after the search; the result ends in a.O or a.Y depending on the number of sweeps and splits (the caller tracks the
 // ping-pong like the per-sweep path does).  Returns 0 or -1 (launch failure).

@@ -64,10 +64,11 @@ class ResultGather:
     The search kernel is persistent (one CTA per SM, ~200 KB of shared memory each); an NCCL collective that overlaps it
     takes SMs away and the step waits for the CTAs that could not start (round 1: 5 % at 8 GPUs).  Frame pairs need no
     exchange at all, so the only transfer -- results to rank 0 -- goes through the copy engines: rank 0 allocates the
-    gather buffer, shares it with the other ranks of the box as a CUDA IPC handle, and every rank copies its slice over
-    NVLink with a device-to-device memcpy (no kernel).  NCCL (or gloo) carries the handle, the barriers and the timing
-    reductions.  If the IPC mapping is not available, the fallback is `dist.gather` to rank 0 (send/recv kernels on a
-    couple of channels); `how` says which one runs.
+    gather buffers and exports them as CUDA IPC handles (libbbme: bbme_ipc_export), every other rank maps them with its own
+    device current (bbme_ipc_open: peer access over NVLink, no context on rank 0's GPU) and pushes its slice with a
+    device-to-device memcpy on its own stream (bbme_copy_async: no kernel).  NCCL (or gloo) carries the 64-byte handles, the
+    barriers and the timing reductions.  If the mapping is not available (CPU tensors, no peer access), the fallback is
+    `dist.gather` to rank 0; `how` says which one runs.
     """
 
     def __init__(self, like, n_total, n_buffers=2, group=None):
@@ -75,47 +76,71 @@ class ResultGather:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.bounds = shard_bounds(n_total, self.world)
-        self.n_local = self.bounds[self.rank][1] - self.bounds[self.rank][0]
-        shape = (n_total,) + tuple(like.shape[1:])
+        self.shape = (n_total,) + tuple(like.shape[1:])
+        self.dtype = like.dtype
+        self.item_bytes = like[0].numel() * like.element_size() if like.shape[0] else 0
         self.how = "nccl gather to rank 0"
-        self.bufs = None       # rank 0: the gather buffers; other ranks: their IPC mappings (or None)
-        self._parts = None
-        self._like = like
+        self.ipc = False
+        self.ptrs = []        # raw device pointers of the gather buffers (rank 0: owned, others: IPC mappings)
+        self.bufs = None      # fallback path: torch tensors on rank 0
+        self._lib = None
+        self._dev = like.device.index if like.is_cuda else None
         if like.is_cuda:
-            try:
-                from torch.multiprocessing.reductions import reduce_tensor
-                payload = [None]
-                if self.rank == 0:
-                    self.bufs = [torch.empty(shape, dtype=like.dtype, device=like.device) for _ in range(n_buffers)]
-                    payload = [[reduce_tensor(b) for b in self.bufs]]
-                dist.broadcast_object_list(payload, src=0, group=group)
-                ok = 1
-                if self.rank != 0:
-                    try:
-                        self.bufs = [fn(*args) for fn, args in payload[0]]
-                    except Exception:
-                        ok = 0
-                flag = torch.tensor([ok], dtype=torch.int32, device=like.device)
-                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-                if int(flag.item()) == 1:
-                    self.how = "copy-engine peer copies over NVLink into rank 0's buffer (CUDA IPC), no communication kernel"
-                elif self.rank != 0:
-                    self.bufs = None
-            except Exception:
-                if self.rank != 0:
-                    self.bufs = None
-        if self.rank == 0 and self.bufs is None:
-            self.bufs = [torch.empty(shape, dtype=like.dtype, device=like.device) for _ in range(n_buffers)]
-        self.ipc = self.how.startswith("copy-engine")
+            self._setup_ipc(like, n_total, n_buffers)
+        if not self.ipc and self.rank == 0:
+            self.bufs = [torch.empty(self.shape, dtype=like.dtype, device=like.device) for _ in range(n_buffers)]
+
+    def _setup_ipc(self, like, n_total, n_buffers):
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        nbytes = n_total * self.item_bytes
+        ok = 1
+        handles = torch.zeros((n_buffers, 64), dtype=torch.uint8)
+        if self.rank == 0:
+            for i in range(n_buffers):
+                p = C.c_void_p()
+                h = (C.c_ubyte * 64)()
+                if lib.bbme_device_alloc(self._dev, nbytes, C.byref(p)) != 0 or lib.bbme_ipc_export(self._dev, p, h) != 0:
+                    ok = 0
+                    break
+                self.ptrs.append(p.value)
+                handles[i] = torch.frombuffer(bytearray(h), dtype=torch.uint8)
+        hd = handles.to(like.device)
+        dist.broadcast(hd, src=0, group=self.group)
+        handles = hd.cpu()
+        if self.rank != 0:
+            for i in range(n_buffers):
+                p = C.c_void_p()
+                h = (C.c_ubyte * 64).from_buffer_copy(bytes(handles[i].tolist()))
+                if lib.bbme_ipc_open(self._dev, h, C.byref(p)) != 0:
+                    ok = 0
+                    break
+                self.ptrs.append(p.value)
+        flag = torch.tensor([ok], dtype=torch.int32, device=like.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        self._lib = lib
+        if int(flag.item()) == 1:
+            self.ipc = True
+            self.how = "copy-engine peer copies over NVLink into rank 0's buffer (CUDA IPC mapping, cudaMemcpyAsync), no communication kernel"
+        else:
+            self._release()
 
     def push(self, local, which=0):
         """Enqueue this rank's slice of gather buffer `which` on the current stream."""
         a, b = self.bounds[self.rank]
         assert local.shape[0] == b - a
-        if self.ipc or (self.rank == 0 and self.world == 1):
-            self.bufs[which][a:b].copy_(local, non_blocking=True)
+        if self.ipc:
+            local = local.contiguous()
+            stream = torch.cuda.current_stream(local.device).cuda_stream
+            rc = self._lib.bbme_copy_async(self._dev, self.ptrs[which] + a * self.item_bytes, local.data_ptr(),
+                                           (b - a) * self.item_bytes, stream)
+            if rc != 0:
+                raise RuntimeError("bbme_copy_async failed")
             return
-        flat = local.contiguous().view(torch.uint8).reshape(local.shape[0], -1)
+        biggest = max(y - x for x, y in self.bounds)  # ragged shards are padded for the collective
+        flat = torch.zeros((biggest, self.item_bytes), dtype=torch.uint8, device=local.device)
+        flat[:b - a] = local.contiguous().view(torch.uint8).reshape(b - a, -1)
         if self.rank == 0:
             parts = [torch.empty_like(flat) for _ in range(self.world)]
             dist.gather(flat, parts, dst=0, group=self.group)
@@ -126,7 +151,34 @@ class ResultGather:
 
     def result(self, which=0):
         """Rank 0, after a barrier that follows every rank's push (and a device synchronisation): the gathered tensor."""
-        return self.bufs[which] if self.rank == 0 else None
+        if self.rank != 0:
+            return None
+        if not self.ipc:
+            return self.bufs[which]
+        out = torch.empty(self.shape, dtype=self.dtype, device=torch.device("cuda", self._dev))
+        stream = torch.cuda.current_stream(out.device).cuda_stream
+        if self._lib.bbme_copy_async(self._dev, out.data_ptr(), self.ptrs[which], out.numel() * out.element_size(), stream) != 0:
+            raise RuntimeError("bbme_copy_async failed")
+        torch.cuda.current_stream(out.device).synchronize()
+        return out
+
+    def _release(self):
+        if self._lib is None:
+            self.ptrs = []
+            return
+        for p in self.ptrs:
+            if self.rank == 0:
+                self._lib.bbme_device_free(self._dev, p)
+            else:
+                self._lib.bbme_ipc_close(self._dev, p)
+        self.ptrs = []
 
     def close(self):
+        """Every rank; the mappings first (call after a barrier), then the owner's buffers."""
+        if self.ipc and self.rank != 0:
+            self._release()
+        if self.ipc:
+            dist.barrier(group=self.group)
+        if self.ipc and self.rank == 0:
+            self._release()
         self.bufs = None

@@ -65,11 +65,11 @@ typedef struct {
   float ms_regularize;     /* all sweeps, splits and fix-up rounds */
   float ms_other;          /* MV upsample + export */
   uint32_t kernel_launches;
-  uint32_t fix_rounds;     /* total fixed-point rounds after the first full sweep pass */
+  uint32_t fix_rounds;     /* fix-up rounds after the first pass of every sweep, summed over sweeps and pairs */
   uint32_t fix_blocks;     /* blocks re-evaluated in those rounds */
   uint32_t search_kernel_used; /* bbme_stage_search only: 1 = generic kernel ran, 2 = TMA kernel ran */
   uint32_t search_launches;    /* search-kernel launches behind ms_search */
-  uint32_t reserved;           /* fix_blocks that were re-evaluated in the per-pair tail loop (the rest ran grid-wide) */
+  uint32_t reserved;
   uint64_t search_candidates; /* in-bounds candidate positions evaluated (== oracle search_sad_calls) */
   uint64_t search_absdiffs;   /* pixels |a-b| in the search (== oracle search_absdiffs) */
 } bbme_stats;
@@ -218,6 +218,19 @@ int bbme_pool_plan(bbme_pool* pool, int width, int height, int num_levels, const
                    const bbme_options* opt, bbme_shape* out);
 int bbme_pool_estimate_batch(bbme_pool* pool, int n, const uint8_t* const* im1, const uint8_t* const* im2,
                              size_t pitch_bytes, float* const* flow);
+
+/* ---- results of the other ranks without a communication kernel (one process per GPU, e.g. under torchrun) ----
+ * The path has no data exchange between pairs; what a multi-process job may still want is every rank's fields in ONE place.
+ * The owner allocates a buffer (bbme_device_alloc) and exports it (bbme_ipc_export: a 64-byte cudaIpcMemHandle_t that travels
+ * through any channel, e.g. an NCCL / gloo broadcast); every other rank maps it with ITS OWN device current (bbme_ipc_open: peer
+ * access over NVLink, no context on the owner's GPU) and pushes its slice with bbme_copy_async -- a copy-engine transfer that
+ * takes no SM from the persistent search kernel, unlike a collective's kernels.  `device` is the calling rank's device. */
+int bbme_device_alloc(int device, size_t bytes, void** p);
+void bbme_device_free(int device, void* p);
+int bbme_ipc_export(int device, void* p, unsigned char* handle64);
+int bbme_ipc_open(int device, const unsigned char* handle64, void** p);
+int bbme_ipc_close(int device, void* p);
+int bbme_copy_async(int device, void* dst, const void* src, size_t bytes, void* stream);
 
 /* Pinned host memory for asynchronous copies. */
 int bbme_host_alloc(void** p, size_t bytes);

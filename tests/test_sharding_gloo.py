@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from blockbasedmotionestimation_b200.shard import gather_fields, my_shard, shard_bounds
+from blockbasedmotionestimation_b200.shard import ResultGather, gather_fields, my_shard, shard_bounds
 from blockbasedmotionestimation_b200.synth import make_pair
 
 
@@ -50,6 +50,17 @@ def _worker(rank, world, port, n_pairs, out_dir):
     assert (on0 is None) == (rank != 0)
     if rank == 0:
         assert torch.equal(on0, full)
+    # the bench's per-step gather on rank 0 (on CPU tensors: the dist.gather path; on GPUs it maps rank 0's buffer over IPC)
+    rg = ResultGather(local, n_pairs, n_buffers=2)
+    assert not rg.ipc and "gather" in rg.how
+    for which in (0, 1):
+        rg.push(local, which)
+    dist.barrier()
+    if rank == 0:
+        assert torch.equal(rg.result(0), full) and torch.equal(rg.result(1), full)
+    else:
+        assert rg.result(0) is None
+    rg.close()
     np.save(os.path.join(out_dir, f"full_{rank}.npy"), full.numpy())
     dist.barrier()
     dist.destroy_process_group()
