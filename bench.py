@@ -536,7 +536,30 @@ def run_ours(args, rank, local_rank, world):
     if not args.no_check and e2e_steps:
         last = hout if ((e2e_steps - 1) & 1) == 0 else hout_b
         e2e_ok = bool(torch.equal(last, dout.cpu()))
-    # ceilings of the host-buffer path on this box (all ranks measure at the same time: the link and the host memory are shared)
+    # ceiling of the host side of the path, measured the same way with the kernels left out: every rank at the same time runs its
+    # H2D copies, compact D2H copies and expansions (bbme_debug_skip_compute), i.e. the link, the pinned staging, the worker
+    # threads and the host memory under the traffic mix of the real arm
+    host_path = None
+    if e2e_steps:
+        lib.bbme_debug_skip_compute(est2._ctx, 1)
+        for k in range(2):
+            step_e2e(k)
+        est2.sync()
+        barrier()
+        t0 = time.perf_counter()
+        hp_steps = max(2, min(e2e_steps, 10))
+        for k in range(hp_steps):
+            step_e2e(k)
+        est2.sync()
+        dt_hp = time.perf_counter() - t0
+        lib.bbme_debug_skip_compute(est2._ctx, 0)
+        thp = torch.tensor([dt_hp], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(thp, op=dist.ReduceOp.MAX)
+        host_path = world * P * hp_steps / float(thp.item())
+        step_e2e(0)  # leave real fields in the host buffers again (the check below already ran)
+        est2.sync()
+    # the individual ceilings (all ranks measure at the same time: the link and the host memory are shared)
     barrier()
     link = est2.measure_host_link(256 << 20) if e2e_steps else None
     if link is not None:
@@ -546,12 +569,14 @@ def run_ours(args, rank, local_rank, world):
             dist.all_reduce(lt, op=dist.ReduceOp.SUM)
         h2d_b, d2h_b, dense_b = 2 * WIDTH * HEIGHT, Hp * Wp, 8 * Hp * Wp
         tot = [float(x) for x in lt.tolist()]
-        ceil_pairs = min(tot[2] * 1e9 / h2d_b, tot[2] * 1e9 / d2h_b, tot[3] * 1e9 / dense_b, value)
+        ceil_pairs = min(tot[2] * 1e9 / h2d_b, tot[2] * 1e9 / d2h_b, tot[3] * 1e9 / dense_b, value, host_path)
         link = {"h2d_gbs_all_ranks": tot[0], "d2h_gbs_all_ranks": tot[1], "duplex_gbs_per_direction_all_ranks": tot[2],
                 "host_stream_write_gbs_all_ranks": tot[3], "host_threads_per_rank": link["host_threads"],
+                "host_path_pairs_per_s": host_path,
+                "host_path_note": "the same host-buffer call on every rank at once with the kernels left out (copies + expansion only): "
+                                  "what the host side of this box sustains for this traffic mix",
                 "ceiling_pairs_per_s": ceil_pairs,
-                "ceiling_note": "min(duplex link / H2D bytes per pair, duplex link / D2H bytes per pair, host write bandwidth / "
-                                "dense field bytes per pair, device-resident value)"}
+                "ceiling_note": "min(host_path_pairs_per_s, device-resident value, and the individually measured link / host-write ceilings)"}
     est2.close()
 
     # ---- the other BASELINE configurations (outside the headline); under N > 1 only the 4K batch, on every rank

@@ -38,6 +38,7 @@ struct Slot {
   uint32_t* hist = nullptr;                // BBME_REG_PROFILE=1: 64 words per level (RegArgs::hist)
   float* out = nullptr;               // device output of the up-sampled path (stripped, sub-sampled field)
   // host-buffer path: the compact int16 field is copied into a pinned staging buffer and expanded on the host
+  cudaEvent_t done_ev = nullptr;  // cudaEventBlockingSync: bbme_sync sleeps instead of spinning (the cores belong to the expansion)
   int16_t* stage[2] = {nullptr, nullptr};
   Ticket* ticket[2] = {nullptr, nullptr};
   int stage_turn = 0;
@@ -81,6 +82,7 @@ struct bbme_ctx {
   uint32_t launches = 0;
   uint32_t search_launches = 0;
   bool stats_armed = false;
+  int skip_compute = 0;  // bbme_debug_skip_compute: host-buffer calls do their copies and expansions but launch no kernel
   int use_graphs = 1;   // small chunks replay a captured CUDA graph of their ~70-230 launches (BBME_GRAPHS=0 disables)
   int next_slot = 0;    // round-robin position over the slots across asynchronous calls
 };
@@ -133,6 +135,7 @@ void release_plan(bbme_ctx* c) {
       if (s.stage[j]) { cudaFreeHost(s.stage[j]); s.stage[j] = nullptr; }
     }
     for (cudaEvent_t e : s.ev) cudaEventDestroy(e);
+    if (s.done_ev) { cudaEventDestroy(s.done_ev); s.done_ev = nullptr; }
     for (auto& g : s.graphs) cudaGraphExecDestroy(g.exec);
     s.graphs.clear();
     if (s.stream && s.own_stream) cudaStreamDestroy(s.stream);
@@ -425,7 +428,13 @@ int collect_after_sync(bbme_ctx* c) {
 }
 
 int sync_all(bbme_ctx* c) {
-  for (Slot& s : c->slots) CUDA_TRY(c, cudaStreamSynchronize(s.stream));
+  for (Slot& s : c->slots) {
+    // a blocking event instead of cudaStreamSynchronize: the calling thread sleeps, it does not spin on a core that the
+    // expansion threads (and, with one process per GPU, the other ranks) can use
+    if (!s.done_ev) CUDA_TRY(c, cudaEventCreateWithFlags(&s.done_ev, cudaEventBlockingSync | cudaEventDisableTiming));
+    CUDA_TRY(c, cudaEventRecord(s.done_ev, s.stream));
+  }
+  for (Slot& s : c->slots) CUDA_TRY(c, cudaEventSynchronize(s.done_ev));
   // host functions are stream-ordered: every expansion has been queued by now; wait for the worker threads
   for (Slot& s : c->slots)
     for (int j = 0; j < 2; ++j)
@@ -753,6 +762,12 @@ int bbme_measure_host_link(bbme_ctx* c, size_t bytes, bbme_host_link* out) {
   return rc;
 }
 
+int bbme_debug_skip_compute(bbme_ctx* c, int on) {
+  if (!c) return BBME_E_ARG;
+  c->skip_compute = on != 0;
+  return BBME_OK;
+}
+
 int bbme_get_stats(bbme_ctx* c, bbme_stats* out) {
   if (!c || !out) return BBME_E_ARG;
   *out = c->stats;
@@ -801,7 +816,7 @@ static int estimate_batch_async_impl(bbme_ctx* c, int n, int factor, const uint8
       for (int i = 0; i < m; ++i)
         CUDA_TRY(c, cudaMemcpyAsync(flow[start + i], s.out + (size_t)i * out_plane, flow_bytes, cudaMemcpyDeviceToHost, s.stream));
     } else {
-      int rc = run_chunk_graphed(c, s, m, s.in1, s.in2, in_pitch, in_plane, nullptr, 0, nullptr, 0, 1);
+      int rc = c->skip_compute ? BBME_OK : run_chunk_graphed(c, s, m, s.in1, s.in2, in_pitch, in_plane, nullptr, 0, nullptr, 0, 1);
       if (rc || (rc = enqueue_dense_result(c, s, m, flow + start))) return rc;
     }
   }

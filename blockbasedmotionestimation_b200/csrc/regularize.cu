@@ -31,20 +31,22 @@ namespace bbme {
 // atomics, push_commit (an iteration later) looks at what they returned and appends.
 struct PushState {
   uint32_t old[4];  // what the stamps held; == ep: nothing to append for that dependent
-  int b;            // index of the block that changed (its dependents are recomputed from it), -1: nothing issued
+  uint32_t pb;      // packed entry (by << 16 | bx) of the block that changed: its dependents are pb + 1, pb + 0x10000 - 1, ...
 };
 
-__device__ __forceinline__ void push_issue(PushState& ps, bool changed, int b, int bx, int by, int gw, int gh, uint32_t* stamp,
+__device__ __forceinline__ void push_issue(PushState& ps, bool changed, int bx, int by, int gw, int gh, uint32_t* stamp,
                                            uint32_t ep) {
   const bool rt = bx + 1 < gw, dn = by + 1 < gh;
+  const int b = by * gw + bx;
   const int d[4] = {b + 1, b + gw - 1, b + gw, b + gw + 1};
   const bool ex[4] = {changed && rt, changed && dn && bx > 0, changed && dn, changed && dn && rt};
 #pragma unroll
   for (int j = 0; j < 4; ++j) ps.old[j] = ex[j] ? atomicExch(&stamp[d[j]], ep) : ep;
-  ps.b = b;
+  ps.pb = ((uint32_t)by << 16) | (uint32_t)bx;
 }
 
-__device__ __forceinline__ void push_commit(const PushState& ps, int gw, uint32_t ep, uint32_t* list, uint32_t* count) {
+// List entries are packed block coordinates (by << 16 | bx; grids are at most 8192 wide): no integer division anywhere.
+__device__ __forceinline__ void push_commit(const PushState& ps, uint32_t ep, uint32_t* list, uint32_t* count) {
   const int lane = threadIdx.x & 31;
   int k = 0;
 #pragma unroll
@@ -61,17 +63,17 @@ __device__ __forceinline__ void push_commit(const PushState& ps, int gw, uint32_
   if (lane == 31) base = atomicAdd(count, (uint32_t)incl);
   base = __shfl_sync(0xffffffffu, base, 31);
   uint32_t pos = base + (uint32_t)(incl - k);
-  const int d[4] = {ps.b + 1, ps.b + gw - 1, ps.b + gw, ps.b + gw + 1};
+  const uint32_t d[4] = {ps.pb + 1u, ps.pb + 0x10000u - 1u, ps.pb + 0x10000u, ps.pb + 0x10000u + 1u};
 #pragma unroll
   for (int j = 0; j < 4; ++j)
-    if (ps.old[j] != ep) list[pos++] = (uint32_t)d[j];
+    if (ps.old[j] != ep) list[pos++] = d[j];
 }
 
 __device__ __forceinline__ void push_dependents(bool changed, int bx, int by, int gw, int gh, uint32_t* stamp,
                                                 uint32_t ep, uint32_t* list, uint32_t* count) {
   PushState ps;
-  push_issue(ps, changed, by * gw + bx, bx, by, gw, gh, stamp, ep);
-  push_commit(ps, gw, ep, list, count);
+  push_issue(ps, changed, bx, by, gw, gh, stamp, ep);
+  push_commit(ps, ep, list, count);
 }
 
 
@@ -247,14 +249,15 @@ __device__ __forceinline__ bool reg_eval_thread(const RegArgs& a, int pair, int 
     unsigned long long M = 1ull;
     int nd = 1;
     s_u[0] = A0;
-#pragma unroll 1
-    for (int i = 0; i < 8; ++i) {
-      if (!has[i]) continue;
-      const uint32_t v = pkin[i];
-      int j = 0;
-      while (j < nd && s_u[j * blockDim.x] != v) ++j;
-      if (j == nd) { s_u[nd * blockDim.x] = v; ++nd; }
-      M += 1ull << (4 * j);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {  // unrolled: pkin / has stay in registers (a rolled loop would index them in local memory)
+      if (has[i]) {
+        const uint32_t v = pkin[i];
+        int j = 0;
+        while (j < nd && s_u[j * blockDim.x] != v) ++j;
+        if (j == nd) { s_u[nd * blockDim.x] = v; ++nd; }
+        M += 1ull << (4 * j);
+      }
     }
     float best = FLT_MAX;
     uint32_t r = A0;
@@ -302,147 +305,6 @@ __device__ __forceinline__ bool reg_eval_thread(const RegArgs& a, int pair, int 
   float best = E0;
   if (E1 < best) { best = E1; r = u1; }
   if (n == 3 && E2 < best) r = u2;
-  *out = r;
-  return true;
-}
-
-// ---- 2x2 / 4x4 blocks in large rounds: the windows travel through shared memory (cp.async), one block ahead ---------------
-// reg_eval_thread waits for its windows: one exposed memory round trip per block at 16 warps per SM is what bounds the
-// sweeps' first passes.  Here the evaluation is cut in two.  small_plan (block i + 1) extracts the distinct vectors and issues
-// cp.async copies of the aligned words that hold the block's rows and every distinct in-image candidate's rows into the
-// thread's column of a two-stage shared-memory ring; small_finish (block i) runs an iteration later, when the copies have
-// landed: SADs from shared memory, energies, winner.  Same arithmetic as reg_eval_thread.
-constexpr int kPlanWords = 28;  // per thread and stage: 4 block rows + 3 candidates x 4 rows x 2 words (2x2 blocks use 14)
-
-struct SmallPlan {
-  uint32_t A0, u1, u2, cur;
-  int b;          // list entry (block index), -1: nothing planned
-  uint32_t bits;  // n (2 bits) | more << 2 | in0 << 3 | in1 << 4 | in2 << 5 | m0 << 8 | m1 << 12 | m2 << 16 | sh0 << 20 | sh1 << 22 | sh2 << 24 | blkhalf << 26
-};
-
-__device__ __forceinline__ void cp_async4(uint32_t* smem_dst, const void* gsrc) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <int BS>  // 2 or 4; ring: this thread's column of the stage, word w at ring[w * blockDim.x]
-__device__ __forceinline__ void small_plan(SmallPlan& pl, const RegArgs& a, int pair, int b, int bx, int by, uint32_t A0,
-                                           const uint32_t (&pkin)[8], uint32_t cur, bool live, uint32_t* ring) {
-  const int gw = a.gw, gh = a.gh;
-  const bool up = by > 0, dn = by < gh - 1, lf = bx > 0, rt = bx < gw - 1;
-  const bool has[8] = {lf, rt, dn && rt, up && lf, up && rt, up, dn, dn && lf};
-  uint32_t u1 = A0, u2 = A0;
-  int n = 1, m0 = 1, m1 = 0, m2 = 0;
-  bool more = false;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const uint32_t v = pkin[i];
-    if (has[i]) {
-      if (v == A0) ++m0;
-      else if (n >= 2 && v == u1) ++m1;
-      else if (n >= 3 && v == u2) ++m2;
-      else if (n == 1) { u1 = v; m1 = 1; n = 2; }
-      else if (n == 2) { u2 = v; m2 = 1; n = 3; }
-      else more = true;
-    }
-  }
-  pl.A0 = A0; pl.u1 = u1; pl.u2 = u2; pl.cur = cur; pl.b = b;
-  const int x = bx * BS, y = by * BS;
-  const int w = a.i1.w, h = a.i1.h, pitch = a.i1.pitch;
-  const bool in0 = (unsigned)(x + mv_x(A0)) <= (unsigned)(w - BS) && (unsigned)(y + mv_y(A0)) <= (unsigned)(h - BS);
-  const bool in1 = n >= 2 && (unsigned)(x + mv_x(u1)) <= (unsigned)(w - BS) && (unsigned)(y + mv_y(u1)) <= (unsigned)(h - BS);
-  const bool in2 = n >= 3 && (unsigned)(x + mv_x(u2)) <= (unsigned)(w - BS) && (unsigned)(y + mv_y(u2)) <= (unsigned)(h - BS);
-  const uint8_t* blk = a.i1.p + (size_t)pair * a.i1.plane + (size_t)y * pitch + x;
-  const uint8_t* ref = a.i2.p + (size_t)pair * a.i2.plane;
-  uint32_t sh[3] = {0, 0, 0};
-  const bool go = live && n > 1 && !more;
-  if (go) {
-    const uint8_t* bq = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(blk) & ~(uintptr_t)3);
-#pragma unroll
-    for (int r = 0; r < BS; ++r) cp_async4(ring + r * blockDim.x, bq + (size_t)r * pitch);
-    const uint32_t uu[3] = {A0, u1, u2};
-    const bool in[3] = {in0, in1, in2};
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      if (in[j]) {
-        const uint8_t* wp = ref + (size_t)(y + mv_y(uu[j])) * pitch + (x + mv_x(uu[j]));
-        const uintptr_t ab = reinterpret_cast<uintptr_t>(wp);
-        sh[j] = (uint32_t)(ab & 3);
-        const uint8_t* q = reinterpret_cast<const uint8_t*>(ab & ~(uintptr_t)3);
-        // the second word of a row is needed when the row runs past the first one (it is inside the row pitch / buffer slack)
-        const bool two = BS == 2 ? sh[j] == 3u : sh[j] != 0u;
-#pragma unroll
-        for (int r = 0; r < BS; ++r) {
-          uint32_t* dst = ring + (4 + (j * 4 + r) * 2) * blockDim.x;
-          cp_async4(dst, q + (size_t)r * pitch);
-          if (two) cp_async4(dst + blockDim.x, q + (size_t)r * pitch + 4);
-        }
-      }
-    }
-  }
-  cp_async_commit();  // every thread commits a (possibly empty) group per plan: wait_group counts groups
-  pl.bits = (uint32_t)n | (more ? 4u : 0u) | (in0 ? 8u : 0u) | (in1 ? 16u : 0u) | (in2 ? 32u : 0u) | ((uint32_t)m0 << 8) |
-            ((uint32_t)m1 << 12) | ((uint32_t)m2 << 16) | (sh[0] << 20) | (sh[1] << 22) | (sh[2] << 24) |
-            ((uint32_t)((reinterpret_cast<uintptr_t>(blk) >> 1) & 1) << 26);
-}
-
-// Returns false if the block has four or more distinct vectors (deferred by the caller); *out = the new vector otherwise.
-template <int BS>
-__device__ __forceinline__ bool small_finish(const SmallPlan& pl, const RegArgs& a, const uint32_t* ring, uint32_t* out) {
-  const int n = (int)(pl.bits & 3u);
-  *out = pl.A0;
-  if (n == 1 && !(pl.bits & 4u)) return true;
-  if (pl.bits & 4u) return false;
-  const bool in0 = pl.bits & 8u, in1 = pl.bits & 16u, in2 = pl.bits & 32u;
-  const int m0 = (pl.bits >> 8) & 15, m1 = (pl.bits >> 12) & 15, m2 = (pl.bits >> 16) & 15;
-  const uint32_t A0 = pl.A0, u1 = pl.u1, u2 = pl.u2;
-  const int x0 = mv_x(A0), y0 = mv_y(A0), x1 = mv_x(u1), y1 = mv_y(u1), x2 = mv_x(u2), y2 = mv_y(u2);
-  const int d01 = abs(x0 - x1) + abs(y0 - y1), d02 = abs(x0 - x2) + abs(y0 - y2), d12 = abs(x1 - x2) + abs(y1 - y2);
-  const float S[3] = {(float)(m1 * d01 + m2 * d02), (float)(m0 * d01 + m2 * d12), (float)(m0 * d02 + m1 * d12)};
-  // the block's rows
-  uint32_t Ab[BS == 2 ? 1 : 4];
-  if (BS == 2) {
-    const uint32_t hs = ((pl.bits >> 26) & 1u) * 16u;  // the 2-byte row is the low or the high half of its aligned word
-    Ab[0] = ((ring[0] >> hs) & 0xffffu) | (((ring[blockDim.x] >> hs) & 0xffffu) << 16);
-  } else {
-#pragma unroll
-    for (int r = 0; r < (BS == 2 ? 1 : 4); ++r) Ab[r] = ring[r * blockDim.x];
-  }
-  const bool in[3] = {in0, in1, in2};
-  float E[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    if (in[j]) {
-      const uint32_t sh = (pl.bits >> (20 + 2 * j)) & 3u;
-      const bool two = BS == 2 ? sh == 3u : sh != 0u;
-      uint32_t sad = 0;
-      if (BS == 2) {
-        uint32_t rr[2];
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const uint32_t* src = ring + (4 + (j * 4 + r) * 2) * blockDim.x;
-          const uint32_t w0 = src[0], w1 = two ? src[blockDim.x] : 0u;
-          rr[r] = __funnelshift_r(w0, w1, sh * 8u) & 0xffffu;
-        }
-        sad = sad4(Ab[0], rr[0] | (rr[1] << 16), 0u);
-      } else {
-#pragma unroll
-        for (int r = 0; r < (BS == 2 ? 1 : 4); ++r) {
-          const uint32_t* src = ring + (4 + (j * 4 + r) * 2) * blockDim.x;
-          const uint32_t w0 = src[0], w1 = two ? src[blockDim.x] : 0u;
-          sad = sad4(Ab[r % (BS == 2 ? 1 : 4)], __funnelshift_r(w0, w1, sh * 8u), sad);
-        }
-      }
-      E[j] = __fadd_rn(__uint2float_rn(sad), __fmul_rn(a.lm, S[j]));
-    }
-  }
-  uint32_t r = A0;
-  float best = E[0];
-  if (E[1] < best) { best = E[1]; r = u1; }
-  if (n == 3 && E[2] < best) r = u2;
   *out = r;
   return true;
 }
@@ -718,13 +580,14 @@ __device__ __forceinline__ void level_classify(const RegArgs& a, int pair, const
       uint32_t* dst = list + base + (uint32_t)(incl - k);
 #pragma unroll
       for (int q = 0; q < 16; ++q)
-        if ((work >> q) & 1u) *dst++ = (uint32_t)((by0 + (q >> 2)) * gw + bx + (q & 3));
+        if ((work >> q) & 1u) *dst++ = ((uint32_t)(by0 + (q >> 2)) << 16) | (uint32_t)(bx + (q & 3));
     }
   } else {
     const uint32_t nb = (uint32_t)gw * gh;
     const uint32_t limit = (nb + 31u) / 32u * 32u;
     for (uint32_t t = lc.gtid; t < limit; t += lc.gthreads) {
       bool work = false;
+      uint32_t packed = 0;
       if (t < nb) {
         const int by = (int)(t / gw), bx = (int)(t - (uint32_t)by * gw);
         const int ru = max(by - 1, 0) * gw, rm = by * gw, rd = min(by + 1, gh - 1) * gw;
@@ -736,6 +599,7 @@ __device__ __forceinline__ void level_classify(const RegArgs& a, int pair, const
         for (int j = 0; j < 8; ++j) same = same && v[j] == k0;
         Y[t] = k0;
         work = !same;
+        packed = ((uint32_t)by << 16) | (uint32_t)bx;
       }
       const uint32_t m = __ballot_sync(0xffffffffu, work);
       if (m) {
@@ -743,7 +607,7 @@ __device__ __forceinline__ void level_classify(const RegArgs& a, int pair, const
         uint32_t base = 0;
         if (lane == leader) base = atomicAdd(&lc.cnt[0], (uint32_t)__popc(m));
         base = __shfl_sync(0xffffffffu, base, leader);
-        if (work) list[base + __popc(m & ((1u << lane) - 1u))] = t;
+        if (work) list[base + __popc(m & ((1u << lane) - 1u))] = packed;
       }
     }
   }
@@ -755,7 +619,7 @@ __device__ __forceinline__ void level_classify(const RegArgs& a, int pair, const
 // path; a small round (the fix-up tail, where a thread has at most a couple of blocks) evaluates them in line and saves the barrier.
 template <int BSK, bool MULTI>
 __device__ __forceinline__ void level_sweep(const RegArgs& a, int pair, const LevelCtx& lc, uint32_t& ep, uint32_t& rounds,
-                                            uint32_t& blocks, uint32_t* s_u, uint32_t* ring) {
+                                            uint32_t& blocks, uint32_t* s_u) {
   const short2* O = a.O + (size_t)pair * a.mv_plane;
   short2* Y = a.Y + (size_t)pair * a.mv_plane;
   uint32_t* Yu = reinterpret_cast<uint32_t*>(Y);
@@ -792,66 +656,7 @@ __device__ __forceinline__ void level_sweep(const RegArgs& a, int pair, const Le
     uint32_t* dcount = &lc.cnt[3 + (r & 1)];
     const bool in_line = cnt <= 2u * lc.gthreads;  // the same for every thread of the cluster
     ++ep;
-    if (BSK <= 4 && !in_line) {
-      // Large round of 2x2 / 4x4 blocks: three-deep software pipeline.  Iteration i: the list entry of block i + 3 and the
-      // vectors of block i + 2 are requested, block i + 1 is planned (its window copies start), block i is finished from
-      // shared memory.  Blocks with four or more distinct vectors go to the second pass.
-      constexpr int BS = BSK <= 2 ? 2 : 4;
-      const uint32_t limit = (cnt + 31u) / 32u * 32u;  // whole warps iterate together
-      const uint32_t G = lc.gthreads;
-      auto entry = [&](uint32_t e) -> int { return e < limit ? (int)lcur[e < cnt ? e : cnt - 1] : 0; };
-      uint32_t e = lc.gtid;            // entry index of the block that is FINISHED in the current iteration
-      // prologue: plan block e, gather block e + G, load entry e + 2G
-      SmallPlan pl, pn;
-      pl.b = -1;
-      int bg = entry(e);               // block whose vectors are gathered next
-      uint32_t Ag = 0, pkg[8], curg = 0;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) pkg[i] = 0;
-      if (e < limit) {
-        small_gather(a, O, Y, bg % a.gw, bg / a.gw, Ag, pkg, curg);
-        small_plan<BS>(pl, a, pair, bg, bg % a.gw, bg / a.gw, Ag, pkg, curg, e < cnt, ring);
-      }
-      bg = entry(e + G);
-      if (e + G < limit) small_gather(a, O, Y, bg % a.gw, bg / a.gw, Ag, pkg, curg);
-      int be = entry(e + 2 * G);       // list entry two blocks ahead
-      PushState ps;
-      ps.b = -1;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) ps.old[j] = ep;
-      int stage = 0;
-      for (; e < limit; e += G) {
-        const bool live = e < cnt;
-        // plan the next block into the other stage, then request the vectors of the one after it
-        const bool has_next = e + G < limit;
-        if (has_next) small_plan<BS>(pn, a, pair, bg, bg % a.gw, bg / a.gw, Ag, pkg, curg, e + G < cnt, ring + (stage ^ 1) * kPlanWords * blockDim.x);
-        else cp_async_commit();
-        bg = be;
-        if (e + 2 * G < limit) small_gather(a, O, Y, bg % a.gw, bg / a.gw, Ag, pkg, curg);
-        be = entry(e + 3 * G);
-        cp_async_wait<1>();            // everything but the newest group has landed: this block's windows are in the ring
-        const int b = pl.b;
-        const int bx = b % a.gw, by = b / a.gw;
-        uint32_t nv = 0;
-        const bool done = !live || small_finish<BS>(pl, a, ring + stage * kPlanWords * blockDim.x, &nv);
-        const uint32_t dm = __ballot_sync(0xffffffffu, !done);
-        if (dm) {
-          uint32_t dbase = 0;
-          const int leader = __ffs(dm) - 1;
-          if (lane == leader) dbase = atomicAdd(dcount, (uint32_t)__popc(dm));
-          dbase = __shfl_sync(0xffffffffu, dbase, leader);
-          if (!done) dlist[dbase + __popc(dm & ((1u << lane) - 1u))] = (uint32_t)b;
-        }
-        const bool changed = live && done && nv != pl.cur;
-        if (changed) Yu[b] = nv;
-        push_commit(ps, a.gw, ep, lnext, next_count);
-        push_issue(ps, changed, b, bx, by, a.gw, a.gh, stamp, ep);
-        pl = pn;
-        stage ^= 1;
-      }
-      cp_async_wait<0>();
-      push_commit(ps, a.gw, ep, lnext, next_count);
-    } else if (BSK >= 8 && in_line) {
+    if (BSK >= 8 && in_line) {
       // A small round of large blocks is a latency problem, not a throughput problem: a team of lanes per block (one window
       // row per lane, all distinct candidates in one or two round trips) instead of one thread walking through 16 rows of
       // every candidate.
@@ -861,8 +666,9 @@ __device__ __forceinline__ void level_sweep(const RegArgs& a, int pair, const Le
       const uint32_t limit = (cnt + TPW - 1) / TPW * TPW;
       for (uint32_t e = team; e < limit; e += nteams) {
         const bool live = e < cnt;
-        const int b = (int)lcur[live ? e : cnt - 1];
-        const int bx = b % a.gw, by = b / a.gw;
+        const uint32_t pb = lcur[live ? e : cnt - 1];
+        const int bx = (int)(pb & 0xffffu), by = (int)(pb >> 16);
+        const int b = by * a.gw + bx;
         bool valid = false;
         const uint32_t my = team_slot_load(a, O, Y, bx, by, (int)tl, valid);
         const uint32_t nv = reg_eval_team_lean<BSK <= 4 ? 8 : BSK>(a, pair, bx, by, (int)tl, live, my, valid);
@@ -896,9 +702,9 @@ __device__ __forceinline__ void level_sweep(const RegArgs& a, int pair, const Le
       uint32_t A1 = 0, pk1[8], cur1 = 0;
 #pragma unroll
       for (int i = 0; i < 8; ++i) pk1[i] = 0;
-      if (r1 < run_limit) small_gather(a, O, Y, b1 % a.gw, b1 / a.gw, A1, pk1, cur1);
+      if (r1 < run_limit) small_gather(a, O, Y, b1 & 0xffff, b1 >> 16, A1, pk1, cur1);
       PushState ps;  // the previous iteration's stamp exchanges, committed after this iteration's evaluation
-      ps.b = -1;
+      ps.pb = 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) ps.old[j] = ep;
       while (r1 < run_limit) {
@@ -912,8 +718,9 @@ __device__ __forceinline__ void level_sweep(const RegArgs& a, int pair, const Le
         b1 = b2; r1 = r2; k1 = k2;
         advance(r2, k2);
         b2 = load_entry(r2, k2);
-        if (r1 < run_limit) small_gather(a, O, Y, b1 % a.gw, b1 / a.gw, A1, pk1, cur1);
-        const int bx = b % a.gw, by = b / a.gw;
+        if (r1 < run_limit) small_gather(a, O, Y, b1 & 0xffff, b1 >> 16, A1, pk1, cur1);
+        const int bx = b & 0xffff, by = b >> 16;  // list entries are packed coordinates
+        const int idx = by * a.gw + bx;
         uint32_t nv = 0;
         const bool done = !live || reg_eval_thread<BSK>(a, pair, bx, by, A0, pk, &nv, in_line, s_u);
         if (!in_line) {
@@ -927,12 +734,12 @@ __device__ __forceinline__ void level_sweep(const RegArgs& a, int pair, const Le
           }
         }
         const bool changed = live && done && nv != cur;
-        if (changed) Yu[b] = nv;
+        if (changed) Yu[idx] = nv;
         if (live && done && b1 == b + 1 && bx + 1 < a.gw) pk1[0] = nv;  // the next block's left neighbour is this block
-        push_commit(ps, a.gw, ep, lnext, next_count);                  // the previous block's dependents
-        push_issue(ps, changed, b, bx, by, a.gw, a.gh, stamp, ep);      // this block's stamp exchanges fly during the next evaluation
+        push_commit(ps, ep, lnext, next_count);                     // the previous block's dependents
+        push_issue(ps, changed, bx, by, a.gw, a.gh, stamp, ep);       // this block's stamp exchanges fly during the next evaluation
       }
-      push_commit(ps, a.gw, ep, lnext, next_count);
+      push_commit(ps, ep, lnext, next_count);
     }
     if (!in_line) {
       // second pass of a large round: the blocks with four or more distinct candidate vectors
@@ -943,8 +750,9 @@ __device__ __forceinline__ void level_sweep(const RegArgs& a, int pair, const Le
       const uint32_t dlimit = (dcnt + 31u) / 32u * 32u;
       for (uint32_t e = lc.gtid; e < dlimit; e += lc.gthreads) {
         const bool live = e < dcnt;
-        const int b = (int)dlist[live ? e : dcnt - 1];
-        const int bx = b % a.gw, by = b / a.gw;
+        const uint32_t pb = dlist[live ? e : dcnt - 1];
+        const int bx = (int)(pb & 0xffffu), by = (int)(pb >> 16);
+        const int b = by * a.gw + bx;
         uint32_t A0, pk[8], cur, nv = 0;
         small_gather(a, O, Y, bx, by, A0, pk, cur);
         if (live) reg_eval_thread<BSK>(a, pair, bx, by, A0, pk, &nv, true, s_u);
@@ -975,8 +783,6 @@ __global__ void __launch_bounds__(kLevelThreads, 1) k_reg_level(RegArgs a, int s
   __shared__ uint32_t s_cnt[8];
   __shared__ uint32_t s_ucol[9 * kLevelThreads];  // per-thread columns of distinct candidate vectors (reg_eval_thread)
   uint32_t* s_u = s_ucol + threadIdx.x;
-  extern __shared__ __align__(16) uint32_t s_ring[];  // 2 stages x kPlanWords x threads: the window ring of small_plan / small_finish
-  uint32_t* ring = s_ring + threadIdx.x;
   LevelCtx lc;
   int pair;
   if (MULTI) {
@@ -1008,11 +814,11 @@ __global__ void __launch_bounds__(kLevelThreads, 1) k_reg_level(RegArgs a, int s
     for (int sw = first_mult; sw < first_mult + sweeps; ++sw) {
       a.lm = lambda * (float)sw;  // lambda * (float)lambda_multiplier, motion_framework.cpp:607
       switch (g >= 32 ? 32 : g) {
-        case 32: level_sweep<32, MULTI>(a, pair, lc, ep, rounds, blocks, s_u, ring); break;
-        case 16: level_sweep<16, MULTI>(a, pair, lc, ep, rounds, blocks, s_u, ring); break;
-        case 8: level_sweep<8, MULTI>(a, pair, lc, ep, rounds, blocks, s_u, ring); break;
-        case 4: level_sweep<4, MULTI>(a, pair, lc, ep, rounds, blocks, s_u, ring); break;
-        default: level_sweep<2, MULTI>(a, pair, lc, ep, rounds, blocks, s_u, ring); break;
+        case 32: level_sweep<32, MULTI>(a, pair, lc, ep, rounds, blocks, s_u); break;
+        case 16: level_sweep<16, MULTI>(a, pair, lc, ep, rounds, blocks, s_u); break;
+        case 8: level_sweep<8, MULTI>(a, pair, lc, ep, rounds, blocks, s_u); break;
+        case 4: level_sweep<4, MULTI>(a, pair, lc, ep, rounds, blocks, s_u); break;
+        default: level_sweep<2, MULTI>(a, pair, lc, ep, rounds, blocks, s_u); break;
       }
       const short2* t = a.O; a.O = a.Y; a.Y = const_cast<short2*>(t);
     }
@@ -1070,17 +876,7 @@ int launch_reg_level(const RegArgs& a, int sweeps, float lambda0, int first_mult
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(n * cs));
   cfg.blockDim = dim3(kLevelThreads);
-  const size_t ring_bytes = (size_t)2 * kPlanWords * kLevelThreads * sizeof(uint32_t);
-  static bool attr_set[64] = {};  // per device: the kernels' opt-in to more than 48 KB of dynamic shared memory
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    if (cudaFuncSetAttribute(k_reg_level<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(k_reg_level<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes) != cudaSuccess)
-      return -1;
-    attr_set[dev] = true;
-  }
-  cfg.dynamicSmemBytes = ring_bytes;
+  cfg.dynamicSmemBytes = 0;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1091,7 +887,7 @@ int launch_reg_level(const RegArgs& a, int sweeps, float lambda0, int first_mult
   cfg.numAttrs = 1;
   cudaError_t e;
   if (cs == 1) {
-    k_reg_level<false><<<n, kLevelThreads, ring_bytes, s>>>(a, sweeps, lambda0, first_mult, single_stage);
+    k_reg_level<false><<<n, kLevelThreads, 0, s>>>(a, sweeps, lambda0, first_mult, single_stage);
     e = cudaGetLastError();
   } else {
     e = cudaLaunchKernelEx(&cfg, k_reg_level<true>, a, sweeps, lambda0, first_mult, single_stage);

@@ -236,6 +236,11 @@ int bbme_copy_async(int device, void* dst, const void* src, size_t bytes, void* 
 int bbme_host_alloc(void** p, size_t bytes);
 void bbme_host_free(void* p);
 
+/* Measurement aid: with `on` != 0, bbme_estimate_batch[_async] performs its host<->device copies and the host-side expansion
+ * but launches no kernel (the fields written are whatever the last real call left on the device).  Timing that call gives the
+ * ceiling of the host side of the path -- link, pinned staging, worker threads, host memory -- under the same traffic mix. */
+int bbme_debug_skip_compute(bbme_ctx* ctx, int on);
+
 /* ---- state of the last bbme_estimate* call on slot 0, for per-stage parity tests (host output buffers) ---- */
 /* frame: 0 = image1, 1 = image2.  out: level_height x level_width bytes, dense. */
 int bbme_debug_level_image(bbme_ctx* ctx, int pair, int frame, int level, uint8_t* out);

@@ -66,3 +66,21 @@ def test_mf_cache_reuses_contexts(oracle):
     assert b"multiples of the block size" in lib.bbme_last_error(bad)
     lib.bbme_mf_close(bad)
     lib.bbme_mf_cache_clear()
+
+
+def test_skip_compute_is_only_a_measurement_aid(oracle):
+    """bbme_debug_skip_compute: copies and expansion without kernels (the bench's host-path ceiling); switching it off restores
+    the real path."""
+    lib = _lib.load()
+    h, w, ss, bs = 96, 128, [24, 24], [8, 8]
+    f1, f2 = make_pair(h, w, 123)
+    want, _ = oracle.estimate(f1, f2, ss, bs, 2)
+    with bb.Estimator(w, h, ss, bs) as est:
+        assert np.array_equal(est.estimate(f1, f2), want)
+        assert lib.bbme_debug_skip_compute(est._ctx, 1) == 0
+        g1, g2 = make_pair(h, w, 124, shift=(-4, 3))
+        stale = est.estimate(g1, g2)          # no kernel ran: the field of the previous call, expanded again
+        assert np.array_equal(stale, want)
+        assert lib.bbme_debug_skip_compute(est._ctx, 0) == 0
+        want2, _ = oracle.estimate(g1, g2, ss, bs, 2)
+        assert np.array_equal(est.estimate(g1, g2), want2)
