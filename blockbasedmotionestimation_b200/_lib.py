@@ -96,6 +96,7 @@ SIGNATURES = {
     "bbme_host_alloc": (_I, [C.POINTER(_P), _SZ]),
     "bbme_host_free": (None, [_P]),
     "bbme_debug_skip_compute": (_I, [_P, _I]),
+    "bbme_debug_set_stamp_epoch": (_I, [_P, C.c_uint32]),
     "bbme_debug_level_image": (_I, [_P, _I, _I, _I, _P]),
     "bbme_debug_level_mv": (_I, [_P, _I, _I, _I, _P]),
     "bbme_stage_pyrdown": (_I, [_P, _P, _I, _I, _P]),

@@ -403,12 +403,18 @@ class Pool:
         except Exception:
             pass
 
-    def estimate_batch(self, im1_list, im2_list):
+    def estimate_batch(self, im1_list, im2_list, out_list=None):
+        """out_list: optional C-contiguous float32 (padded_h, padded_w, 2) arrays to fill (reused buffers avoid the page faults
+        of fresh ones; pinned buffers from bbme_host_alloc make the copies asynchronous)."""
         n = len(im1_list)
         h, w = self.shape["height"], self.shape["width"]
         PA = C.c_void_p * n
         p1, p2, po = PA(), PA(), PA()
-        outs = [np.empty((self.shape["padded_height"], self.shape["padded_width"], 2), np.float32) for _ in range(n)]
+        fshape = (self.shape["padded_height"], self.shape["padded_width"], 2)
+        outs = out_list if out_list is not None else [np.empty(fshape, np.float32) for _ in range(n)]
+        for o in outs:
+            if o.dtype != np.float32 or o.shape != fshape or not o.flags["C_CONTIGUOUS"]:
+                raise BbmeError(-1, "flow buffers must be C-contiguous float32 (padded_h, padded_w, 2)")
         keep = []
         for i in range(n):
             a = np.ascontiguousarray(im1_list[i], np.uint8)

@@ -762,6 +762,21 @@ int bbme_measure_host_link(bbme_ctx* c, size_t bytes, bbme_host_link* out) {
   return rc;
 }
 
+int bbme_debug_set_stamp_epoch(bbme_ctx* c, uint32_t epoch) {
+  if (!c) return BBME_E_ARG;
+  if (!c->planned) return BBME_E_STATE;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  int rc = sync_all(c);
+  if (rc) return rc;
+  for (Slot& s : c->slots) {
+    std::vector<uint32_t> ctr((size_t)c->opt.chunk_pairs * kCtrWords, 0u);
+    CUDA_TRY(c, cudaMemcpy(ctr.data(), s.ctr, ctr.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (int p = 0; p < c->opt.chunk_pairs; ++p) ctr[(size_t)p * kCtrWords + CTR_EPOCH] = epoch;
+    CUDA_TRY(c, cudaMemcpy(s.ctr, ctr.data(), ctr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  }
+  return BBME_OK;
+}
+
 int bbme_debug_skip_compute(bbme_ctx* c, int on) {
   if (!c) return BBME_E_ARG;
   c->skip_compute = on != 0;

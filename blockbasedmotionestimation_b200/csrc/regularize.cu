@@ -493,7 +493,7 @@ __device__ __forceinline__ uint32_t reg_eval_team_lean(const RegArgs& a, int pai
 namespace cg = cooperative_groups;
 
 #ifndef BBME_LEVEL_THREADS
-#define BBME_LEVEL_THREADS 512  // threads per CTA of the level kernel (one CTA per SM); 1024 (64 registers) measured slower: spills
+#define BBME_LEVEL_THREADS 640  // threads per CTA of the level kernel (one CTA per SM, 102 registers): 512 and 768 measured 1-5 % slower, 1024 (64 registers, spills) 20 %
 #endif
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -528,6 +528,8 @@ __device__ __forceinline__ void level_classify(const RegArgs& a, int pair, const
     const int gw4 = gw >> 2;
     const uint32_t strips = (uint32_t)gw4 * (uint32_t)((gh + 3) >> 2);
     const uint32_t limit = (strips + 31u) / 32u * 32u;
+    // (Tried: issuing the next strip's six loads before this strip is examined -- slower, the registers it takes cost more than
+    // the doubled bytes in flight bring.)
     for (uint32_t t = lc.gtid; t < limit; t += lc.gthreads) {
       const bool live = t < strips;
       const int st = live ? (int)(t / gw4) : 0, cg = live ? (int)(t - (uint32_t)st * gw4) : 0;

@@ -240,6 +240,9 @@ void bbme_host_free(void* p);
  * but launches no kernel (the fields written are whatever the last real call left on the device).  Timing that call gives the
  * ceiling of the host side of the path -- link, pinned staging, worker threads, host memory -- under the same traffic mix. */
 int bbme_debug_skip_compute(bbme_ctx* ctx, int on);
+/* Test aid: sets the per-pair epoch of the regularisation's de-duplication stamps (a 32-bit counter that grows by a few
+ * hundred per chunk for the lifetime of a plan; the kernel clears the stamps and restarts it before it can wrap). */
+int bbme_debug_set_stamp_epoch(bbme_ctx* ctx, uint32_t epoch);
 
 /* ---- state of the last bbme_estimate* call on slot 0, for per-stage parity tests (host output buffers) ---- */
 /* frame: 0 = image1, 1 = image2.  out: level_height x level_width bytes, dense. */

@@ -1,0 +1,6 @@
+set -x
+D=gpurun_out/r02m; mkdir -p $D
+timeout 900 python -m pytest tests -m gpu -x -q > $D/pytest.log 2>&1; echo "pytest rc=$?" >> $D/pytest.log
+BBME_REG_PROFILE=1 timeout 300 python scripts/reg_profile.py 128 1 > $D/prof128.json 2> $D/prof128.err
+for T in 640 768; do BBME_LIB=$PWD/blockbasedmotionestimation_b200/libbbme_t$T.so timeout 300 python scripts/reg_profile.py 128 1 > $D/prof128_t$T.json 2> $D/prof128_t$T.err; done
+timeout 300 python scripts/reg_profile.py 1 8 > $D/prof1.json 2> $D/prof1.err

@@ -84,3 +84,20 @@ def test_skip_compute_is_only_a_measurement_aid(oracle):
         assert lib.bbme_debug_skip_compute(est._ctx, 0) == 0
         want2, _ = oracle.estimate(g1, g2, ss, bs, 2)
         assert np.array_equal(est.estimate(g1, g2), want2)
+
+
+def test_stamp_epoch_restarts_before_it_wraps(oracle):
+    """The de-duplication stamps of the regularisation carry a 32-bit epoch that grows for the lifetime of a plan (ADVICE round
+    1): just below the wrap the kernel clears the stamps and restarts the epoch, and the field stays exact."""
+    lib = _lib.load()
+    h, w, ss, bs = 128, 192, [24, 24], [8, 8]
+    pairs = [make_pair(h, w, 300 + i, shift=(i - 1, 2 - i), patches=3) for i in range(3)]
+    wants = [oracle.estimate(a, b, ss, bs, 2)[0] for a, b in pairs]
+    with bb.Estimator(w, h, ss, bs, chunk_pairs=3) as est:
+        got = est.estimate_batch([p[0] for p in pairs], [p[1] for p in pairs])
+        assert all(np.array_equal(g, w_) for g, w_ in zip(got, wants))
+        for epoch in (0xf0000001, 0xffffff00, 0xefffffff):
+            assert lib.bbme_debug_set_stamp_epoch(est._ctx, epoch) == 0
+            for _ in range(2):  # the second call runs on the restarted (or still growing) epoch with stale stamps below it
+                got = est.estimate_batch([p[0] for p in pairs], [p[1] for p in pairs])
+                assert all(np.array_equal(g, w_) for g, w_ in zip(got, wants)), hex(epoch)
