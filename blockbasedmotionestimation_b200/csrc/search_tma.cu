@@ -26,6 +26,7 @@
 #include "kernels.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace bbme {
@@ -43,11 +44,12 @@ namespace bbme {
 #ifndef BBME_MINB
 #define BBME_MINB 1
 #endif
-constexpr int kStages = BBME_STAGES;
+constexpr int kStages = BBME_STAGES;   // minimum ring depth: the stage budget (and with it the band split) is sized for this many
+constexpr int kMaxStages = 16;         // the ring takes as many stages as fit the CTA's shared memory, up to this (TmaSearchArgs::stages)
 constexpr int kConsumerWarps = BBME_CW;
 constexpr int kMinCtas = BBME_MINB;
 constexpr int kThreads = 32 * (1 + kConsumerWarps);
-constexpr int kBlockSlots = kStages + 1;
+constexpr int kMaxBlockSlots = kMaxStages + 1;
 
 struct TmaSearchArgs {
   int w, h;            // level size
@@ -67,6 +69,9 @@ struct TmaSearchArgs {
   int rank_off;        // byte offset of the spiral-rank table (uint16, (n + SEG) rows of n) in dynamic shared memory
   int box1_word;       // 0: one window box; else the word column where the second (overlapping) box starts
   int box1_off_words;  // word offset of the second box inside a stage
+  int stage_shift;     // log2(stages) when stages is a power of two, 0 when stages == kStages
+  int stages;          // ring depth of this launch (kStages .. kMaxStages): small units (32x32 blocks with +-16: three work items
+                       // per unit) need a deep ring to keep sixteen consumer warps fed, large windows only fit a shallow one
   short2* mv;
   size_t mv_plane;
   unsigned long long* counters;
@@ -142,7 +147,7 @@ __device__ __forceinline__ void spiral_unrank(uint32_t rank, int& dx, int& dy) {
   else { dy = -r; dx = (o - 6 * r) - r + 1; }
 }
 
-template <int BS, int SEG, int PWW, bool K64>
+template <int BS, int SEG, int PWW, bool K64, bool DEEP>
 __global__ void __launch_bounds__(kThreads, kMinCtas)
 k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant__ CUtensorMap map_blk,
              const TmaSearchArgs a) {
@@ -152,14 +157,21 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
   constexpr int AP = BS >= 16 ? BS : 16;   // staged block row pitch (TMA inner extent is >= 16 bytes)
 
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t s_full[kStages];
-  __shared__ __align__(8) uint64_t s_empty[kStages];
-  __shared__ StageMeta s_meta[kStages];
-  __shared__ uint32_t s_sdone[kStages];
-  __shared__ uint32_t s_bkey[kBlockSlots];
-  __shared__ unsigned long long s_bkey64[kBlockSlots];
-  __shared__ uint32_t s_bdone[kBlockSlots];
-  __shared__ uint32_t s_bbusy[kBlockSlots];
+  __shared__ __align__(8) uint64_t s_full[kMaxStages];
+  __shared__ __align__(8) uint64_t s_empty[kMaxStages];
+  __shared__ StageMeta s_meta[kMaxStages];
+  __shared__ uint32_t s_sdone[kMaxStages];
+  __shared__ uint32_t s_bkey[kMaxBlockSlots];
+  __shared__ unsigned long long s_bkey64[kMaxBlockSlots];
+  __shared__ uint32_t s_bdone[kMaxBlockSlots];
+  __shared__ uint32_t s_bbusy[kMaxBlockSlots];
+  // Ring depth: kStages (compile time) or, in the DEEP instantiations, 8 or 16 stages (shift and mask).  Sixteen consumer warps
+  // want ~16 work items ready; where a unit holds only a few items (32x32 blocks with +-16: three) five stages starve them
+  // (58 % of the integer peak, long-scoreboard stalls), sixteen do not (73 %).  Large-window geometries keep the five stages
+  // they were tuned with -- and the compile-time ring arithmetic: a run-time depth in every instantiation cost config 2 1 %.
+  const int NS = DEEP ? a.stages : kStages, NB = NS + 1, nshift = a.stage_shift;
+  auto ring_slot = [&](int k) -> int { return DEEP ? (k & (NS - 1)) : (k % kStages); };
+  auto ring_turn = [&](int k) -> int { return DEEP ? (k >> nshift) : (k / kStages); };
   __shared__ uint32_t s_next;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -170,13 +182,13 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
   const int my_units = my_blocks * a.nbands;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], 1);
       s_sdone[i] = 0;
       s_meta[i].unit = -1;  // shared memory keeps the previous CTA's values: a stale unit number must not match
     }
-    for (int i = 0; i < kBlockSlots; ++i) {
+    for (int i = 0; i < kMaxBlockSlots; ++i) {
       s_bkey[i] = 0xffffffffu;
       s_bkey64[i] = ~0ull;
       s_bdone[i] = 0;
@@ -201,13 +213,13 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
     // ------------------------------------------------------------------ producer
     if (lane == 0) {
       for (int k = 0; k < my_units; ++k) {
-        const int stage = k % kStages;
-        if (k >= kStages) mbar_wait(&s_empty[stage], (uint32_t)((k / kStages) - 1) & 1u, 1, k);
+        const int stage = ring_slot(k);
+        if (k >= NS) mbar_wait(&s_empty[stage], (uint32_t)(ring_turn(k) - 1) & 1u, 1, k);
         const int lb = k / a.nbands, band = k - lb * a.nbands;
         if (band == 0) {
-          // units complete out of order, so the block that used this key slot kBlockSlots blocks ago may still be in
+          // units complete out of order, so the block that used this key slot NB blocks ago may still be in
           // flight (all its units are already staged, so it will finish without this producer)
-          volatile uint32_t* busy = &s_bbusy[lb % kBlockSlots];
+          volatile uint32_t* busy = &s_bbusy[lb % NB];
           for (uint32_t polls = 0; *busy != 0u; __nanosleep(32))
             if (++polls > (1u << 24)) mbar_stuck(2, k, 0);
           *busy = 1u;
@@ -222,7 +234,7 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
         const int wx_al = wx & ~15;  // floor to a multiple of 16 (two's complement, also for negative wx)
         StageMeta m;
         m.x2 = x2; m.y2 = y2; m.off = wx - wx_al; m.predx = pred.x; m.predy = pred.y;
-        m.valid = valid; m.band = band; m.bslot = lb % kBlockSlots; m.gblk = gblk; m.unit = k;
+        m.valid = valid; m.band = band; m.bslot = lb % NB; m.gblk = gblk; m.unit = k;
         s_meta[stage] = m;
         if (valid) {
           uint8_t* st = smem + (size_t)stage * a.stage_bytes;
@@ -287,9 +299,7 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
   // same parity -- on a fresh barrier even on the "phase before the first".  The unit number in the stage's metadata
   // (written by the producer before it arms the barrier, hence visible once the barrier completes; -1 at start) tells
   // the turns apart.
-  auto wait_unit = [&](int k) {
-    const int st = k % kStages;
-    const uint32_t par = (uint32_t)(k / kStages) & 1u;
+  auto wait_unit = [&](int k, int st, uint32_t par) {
     for (uint32_t polls = 0;; __nanosleep(64)) {
       mbar_wait(&s_full[st], par, 3, k);
       if (*reinterpret_cast<volatile int*>(&s_meta[st].unit) == k) break;
@@ -306,13 +316,18 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
     const int k0 = T0 / IU;                              // unit of lane 0
     const int split = (k0 + 1) * IU - T0;                // lanes [0, split) belong to k0, the rest to k0 + 1
     const int k1 = (split < 32 && k0 + 1 < my_units) ? k0 + 1 : k0;
-    wait_unit(k0);
-    if (k1 != k0) wait_unit(k1);
+    // ring position of k0 once per item; k1 = k0 + 1 follows from it
+    const int st0 = ring_slot(k0);
+    const uint32_t par0 = (uint32_t)ring_turn(k0) & 1u;
+    const int st1 = k1 != k0 ? (st0 + 1 == NS ? 0 : st0 + 1) : st0;
+    const uint32_t par1 = (k1 != k0 && st1 == 0) ? par0 ^ 1u : par0;
+    wait_unit(k0, st0, par0);
+    if (k1 != k0) wait_unit(k1, st1, par1);
 
     const int T = T0 + lane;
     const bool second = lane >= split;
     const int kl = second ? k1 : k0;
-    const int stage = kl % kStages;
+    const int stage = second ? st1 : st0;
     const StageMeta m = s_meta[stage];
     const int q = T - kl * IU;
     const int segs_here = min(a.segs_per_band, a.segs_total - m.band * a.segs_per_band);
@@ -384,20 +399,32 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
       if (K64) {
         // 64-bit key (SAD, spiral rank).  The closed-form rank costs ~25 instructions, so it is NOT computed per
         // candidate: the lane keeps its minimum SAD and the set of candidates attaining it; after the warp has reduced
-        // the SADs, only the lanes that hold the item's minimum rank their (usually single) candidate.
+        // the SADs, only the lanes that hold the item's minimum rank their (usually single) candidate.  (Tried: no bit set
+        // here, the lanes holding the minimum going through their accumulators again after the reduction -- the longer live
+        // range of the accumulators costs more than the 26 instructions saved: config 5 64.6 -> 63.0 %.)
+        if (xok && c_lo == 0 && c_hi == SEG - 1) {  // every candidate of the lane in the image (nearly all lanes): no masking
 #pragma unroll
-        for (int c = 0; c < SEG; ++c) {
-          const bool ok = xok && c >= c_lo && c <= c_hi;
-          best = min(best, ok ? acc[c] : 0xffffffffu);
-        }
+          for (int c = 0; c < SEG; ++c) best = min(best, acc[c]);
 #pragma unroll
-        for (int c = 0; c < SEG; ++c) {
-          const bool ok = xok && c >= c_lo && c <= c_hi;
-          eqmask |= (ok && acc[c] == best) ? (1u << c) : 0u;
+          for (int c = 0; c < SEG; ++c) eqmask |= (acc[c] == best) ? (1u << c) : 0u;
+        } else {
+#pragma unroll
+          for (int c = 0; c < SEG; ++c) {
+            const bool ok = xok && c >= c_lo && c <= c_hi;
+            best = min(best, ok ? acc[c] : 0xffffffffu);
+          }
+#pragma unroll
+          for (int c = 0; c < SEG; ++c) {
+            const bool ok = xok && c >= c_lo && c <= c_hi;
+            eqmask |= (ok && acc[c] == best) ? (1u << c) : 0u;
+          }
         }
         rank_dx = dx;
         rank_dy0 = dyf;
       } else {
+        // (Tried for 8x8 blocks, where the two key instructions and the rank load per candidate are 13 % of an item: bare SAD
+        // minima per lane and keys only in the lanes that hold the item's minimum after a warp reduction -- config 3 fell
+        // from 65 % to 56 % of the integer peak: the 43 accumulators stay live across the reduction and the re-scan diverges.)
         const uint16_t* rk = s_rank + (size_t)(m.band * a.band_rows + cy0) * a.n + o;
         if (xok && c_lo == 0 && c_hi == SEG - 1) {
 #pragma unroll
@@ -436,12 +463,12 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
       }
       __threadfence_block();
       const int n0 = min(32, split);
-      const uint32_t d0 = atomicAdd(&s_sdone[k0 % kStages], (uint32_t)n0);
-      if (d0 + (uint32_t)n0 == (uint32_t)IU) finish_unit(k0 % kStages);
+      const uint32_t d0 = atomicAdd(&s_sdone[st0], (uint32_t)n0);
+      if (d0 + (uint32_t)n0 == (uint32_t)IU) finish_unit(st0);
       if (k1 != k0) {
         const int n1 = 32 - n0;
-        const uint32_t d1 = atomicAdd(&s_sdone[k1 % kStages], (uint32_t)n1);
-        if (d1 + (uint32_t)n1 == (uint32_t)IU) finish_unit(k1 % kStages);
+        const uint32_t d1 = atomicAdd(&s_sdone[st1], (uint32_t)n1);
+        if (d1 + (uint32_t)n1 == (uint32_t)IU) finish_unit(st1);
       }
     }
     __syncwarp();
@@ -507,6 +534,7 @@ struct TmaGeom {
   TmaSearchArgs a;
   int seg;
   int k64;
+  int deep;  // the DEEP instantiation (ring of 8 or 16 stages) runs this geometry
   int box_w, box_h;
   size_t smem;
 };
@@ -577,36 +605,53 @@ static bool make_geom(int w, int h, int bs, int R, TmaGeom* g) {
   g->a.blk_bytes = blk_bytes;
   g->a.box1_word = two_box ? pww - 4 : 0;
   g->a.box1_off_words = two_box ? (int)(one_box / 4) : 0;
-  g->a.rank_off = kStages * g->a.stage_bytes;
+  // as deep a ring as the shared memory holds (the stage size above was chosen for kStages stages)
+  {
+    const size_t rank_b = use_k64 ? 0 : (((size_t)(n + seg) * n * 2 + 127) / 128) * 128;
+    int st = (int)((200 * 1024 - rank_b) / (size_t)g->a.stage_bytes);
+    // sixteen consumer warps want ~16 work items ready: a deep ring where a unit holds few items (32x32 / +-16: three), the
+    // kStages that the large-window geometries were tuned with elsewhere (config 2 measured the same at 5, 8 and 16)
+    const int items_per_unit = (n * spb + 31) / 32;
+    if (items_per_unit * kStages >= 32 || use_k64 || pww > 32) st = kStages;  // DEEP instantiations exist for pitch classes <= 32
+    if (const char* e = getenv("BBME_SEARCH_STAGES")) st = atoi(e);             // tuning runs
+    g->deep = (st >= 8 && !use_k64 && pww <= 32) ? 1 : 0;
+    g->a.stages = !g->deep ? kStages : (st >= 16 ? 16 : 8);
+    g->a.stage_shift = g->a.stages == 16 ? 4 : (g->a.stages == 8 ? 3 : 0);
+  }
+  g->a.rank_off = g->a.stages * g->a.stage_bytes;
   g->smem = (size_t)g->a.rank_off + (use_k64 ? 0 : (((size_t)(n + seg) * n * 2 + 127) / 128) * 128);
   if (g->smem > 200 * 1024) return false;  // ring + rank table must fit the CTA's shared memory: generic kernel instead
   return true;
 }
 
 // One instantiation: a == nullptr prepares it (shared-memory opt-in, once per plan), else launches it.
-template <int BS, int SEG, int PWW, bool K64>
+template <int BS, int SEG, int PWW, bool K64, bool DEEP>
 static int run_inst(const TmaSearchPlan& plan, const TmaSearchArgs* a, int grid, cudaStream_t s) {
   if (!a)
-    return cudaFuncSetAttribute(k_search_tma<BS, SEG, PWW, K64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess ? 1 : -1;
-  k_search_tma<BS, SEG, PWW, K64><<<grid, kThreads, plan.smem_bytes, s>>>(plan.map_win, plan.map_blk, *a);
+    return cudaFuncSetAttribute(k_search_tma<BS, SEG, PWW, K64, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess ? 1 : -1;
+  k_search_tma<BS, SEG, PWW, K64, DEEP><<<grid, kThreads, plan.smem_bytes, s>>>(plan.map_win, plan.map_blk, *a);
   return 1;
 }
 
 // Finds the instantiation of (block size, rows per lane, window pitch class, key width).  Returns 1 = done, 0 = there is none
 // (the caller falls back to the generic kernel at plan time; never silently at launch time), -1 = CUDA error.
-static int dispatch(const TmaSearchPlan& plan, int k64, int pww, const TmaSearchArgs* a, int grid, cudaStream_t s) {
+static int dispatch(const TmaSearchPlan& plan, int k64, int pww, int deep, const TmaSearchArgs* a, int grid, cudaStream_t s) {
 #define BBME_CASE(BS_, SEG_, PWW_) \
-  if (!k64 && plan.bs == BS_ && plan.seg == SEG_ && pww == PWW_) return run_inst<BS_, SEG_, PWW_, false>(plan, a, grid, s);
+  if (!k64 && !deep && plan.bs == BS_ && plan.seg == SEG_ && pww == PWW_) return run_inst<BS_, SEG_, PWW_, false, false>(plan, a, grid, s);
+#define BBME_CASED(BS_, SEG_, PWW_) /* small windows also exist with the deep ring */ \
+  BBME_CASE(BS_, SEG_, PWW_) \
+  if (!k64 && deep && plan.bs == BS_ && plan.seg == SEG_ && pww == PWW_) return run_inst<BS_, SEG_, PWW_, false, true>(plan, a, grid, s);
 #define BBME_CASE64(BS_, SEG_, PWW_) \
-  if (k64 && plan.bs == BS_ && plan.seg == SEG_ && pww == PWW_) return run_inst<BS_, SEG_, PWW_, true>(plan, a, grid, s);
+  if (k64 && plan.bs == BS_ && plan.seg == SEG_ && pww == PWW_) return run_inst<BS_, SEG_, PWW_, true, false>(plan, a, grid, s);
 #define BBME_CASES(BS_, SEG_) \
-  BBME_CASE(BS_, SEG_, 16) BBME_CASE(BS_, SEG_, 24) BBME_CASE(BS_, SEG_, 32) BBME_CASE(BS_, SEG_, 40) \
+  BBME_CASED(BS_, SEG_, 16) BBME_CASED(BS_, SEG_, 24) BBME_CASED(BS_, SEG_, 32) BBME_CASE(BS_, SEG_, 40) \
   BBME_CASE(BS_, SEG_, 48) BBME_CASE(BS_, SEG_, 64)
   BBME_CASES(8, 13) BBME_CASES(8, 11) BBME_CASES(8, 26) BBME_CASES(8, 43) BBME_CASES(16, 13) BBME_CASES(16, 11) BBME_CASES(32, 13) BBME_CASES(32, 11)
   BBME_CASE64(16, 13, 40) BBME_CASE64(16, 13, 64) BBME_CASE64(16, 11, 40) BBME_CASE64(16, 11, 64)
   BBME_CASE64(32, 13, 40) BBME_CASE64(32, 13, 64) BBME_CASE64(32, 11, 40) BBME_CASE64(32, 11, 64)
 #undef BBME_CASE64
 #undef BBME_CASES
+#undef BBME_CASED
 #undef BBME_CASE
   return 0;
 }
@@ -633,10 +678,10 @@ int tma_search_plan(TmaSearchPlan* plan, const uint8_t* img1, const uint8_t* img
   plan->box_h = g.box_h;
   plan->n_box_x = 1;
   plan->threads = kThreads;
-  plan->stages = kStages;
+  plan->stages = g.a.stages;
   plan->smem_bytes = g.smem;
   // the kernel for this geometry must exist NOW: a geometry without an instantiation runs the generic kernel
-  const int have = dispatch(*plan, g.k64, g.a.pww, nullptr, 0, nullptr);
+  const int have = dispatch(*plan, g.k64, g.a.pww, g.deep, nullptr, 0, nullptr);
   if (have < 0) {
     if (err) snprintf(err, errlen, "cudaFuncSetAttribute(max dynamic shared memory) failed for the search kernel");
     return -1;
@@ -658,7 +703,7 @@ int launch_search_tma(const TmaSearchPlan& plan, ImgView i1, ImgView i2, MvView 
   const int total = a.gw * a.gh * n;
   int grid = sm_count * kMinCtas;
   if (grid > total) grid = total;
-  return dispatch(plan, g.k64, a.pww, &a, grid, s) == 1 ? 0 : -1;
+  return dispatch(plan, g.k64, a.pww, g.deep, &a, grid, s) == 1 ? 0 : -1;
 }
 
 }  // namespace bbme
