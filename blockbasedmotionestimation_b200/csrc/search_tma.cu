@@ -49,7 +49,6 @@ constexpr int kMaxStages = 16;         // the ring takes as many stages as fit t
 constexpr int kConsumerWarps = BBME_CW;
 constexpr int kMinCtas = BBME_MINB;
 constexpr int kThreads = 32 * (1 + kConsumerWarps);
-constexpr int kMaxBlockSlots = kMaxStages + 1;
 
 struct TmaSearchArgs {
   int w, h;            // level size
@@ -157,14 +156,15 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
   constexpr int AP = BS >= 16 ? BS : 16;   // staged block row pitch (TMA inner extent is >= 16 bytes)
 
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t s_full[kMaxStages];
-  __shared__ __align__(8) uint64_t s_empty[kMaxStages];
-  __shared__ StageMeta s_meta[kMaxStages];
-  __shared__ uint32_t s_sdone[kMaxStages];
-  __shared__ uint32_t s_bkey[kMaxBlockSlots];
-  __shared__ unsigned long long s_bkey64[kMaxBlockSlots];
-  __shared__ uint32_t s_bdone[kMaxBlockSlots];
-  __shared__ uint32_t s_bbusy[kMaxBlockSlots];
+  constexpr int SMAX = DEEP ? kMaxStages : kStages, BMAX = SMAX + 1;
+  __shared__ __align__(8) uint64_t s_full[SMAX];
+  __shared__ __align__(8) uint64_t s_empty[SMAX];
+  __shared__ StageMeta s_meta[SMAX];
+  __shared__ uint32_t s_sdone[SMAX];
+  __shared__ uint32_t s_bkey[BMAX];
+  __shared__ unsigned long long s_bkey64[BMAX];
+  __shared__ uint32_t s_bdone[BMAX];
+  __shared__ uint32_t s_bbusy[BMAX];
   // Ring depth: kStages (compile time) or, in the DEEP instantiations, 8 or 16 stages (shift and mask).  Sixteen consumer warps
   // want ~16 work items ready; where a unit holds only a few items (32x32 blocks with +-16: three) five stages starve them
   // (58 % of the integer peak, long-scoreboard stalls), sixteen do not (73 %).  Large-window geometries keep the five stages
@@ -182,13 +182,13 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
   const int my_units = my_blocks * a.nbands;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kMaxStages; ++i) {
+    for (int i = 0; i < SMAX; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], 1);
       s_sdone[i] = 0;
       s_meta[i].unit = -1;  // shared memory keeps the previous CTA's values: a stale unit number must not match
     }
-    for (int i = 0; i < kMaxBlockSlots; ++i) {
+    for (int i = 0; i < BMAX; ++i) {
       s_bkey[i] = 0xffffffffu;
       s_bkey64[i] = ~0ull;
       s_bdone[i] = 0;
@@ -299,7 +299,9 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
   // same parity -- on a fresh barrier even on the "phase before the first".  The unit number in the stage's metadata
   // (written by the producer before it arms the barrier, hence visible once the barrier completes; -1 at start) tells
   // the turns apart.
-  auto wait_unit = [&](int k, int st, uint32_t par) {
+  auto wait_unit = [&](int k) {
+    const int st = ring_slot(k);
+    const uint32_t par = (uint32_t)ring_turn(k) & 1u;
     for (uint32_t polls = 0;; __nanosleep(64)) {
       mbar_wait(&s_full[st], par, 3, k);
       if (*reinterpret_cast<volatile int*>(&s_meta[st].unit) == k) break;
@@ -316,18 +318,13 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
     const int k0 = T0 / IU;                              // unit of lane 0
     const int split = (k0 + 1) * IU - T0;                // lanes [0, split) belong to k0, the rest to k0 + 1
     const int k1 = (split < 32 && k0 + 1 < my_units) ? k0 + 1 : k0;
-    // ring position of k0 once per item; k1 = k0 + 1 follows from it
-    const int st0 = ring_slot(k0);
-    const uint32_t par0 = (uint32_t)ring_turn(k0) & 1u;
-    const int st1 = k1 != k0 ? (st0 + 1 == NS ? 0 : st0 + 1) : st0;
-    const uint32_t par1 = (k1 != k0 && st1 == 0) ? par0 ^ 1u : par0;
-    wait_unit(k0, st0, par0);
-    if (k1 != k0) wait_unit(k1, st1, par1);
+    wait_unit(k0);
+    if (k1 != k0) wait_unit(k1);
 
     const int T = T0 + lane;
     const bool second = lane >= split;
     const int kl = second ? k1 : k0;
-    const int stage = second ? st1 : st0;
+    const int stage = ring_slot(kl);
     const StageMeta m = s_meta[stage];
     const int q = T - kl * IU;
     const int segs_here = min(a.segs_per_band, a.segs_total - m.band * a.segs_per_band);
@@ -463,12 +460,12 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
       }
       __threadfence_block();
       const int n0 = min(32, split);
-      const uint32_t d0 = atomicAdd(&s_sdone[st0], (uint32_t)n0);
-      if (d0 + (uint32_t)n0 == (uint32_t)IU) finish_unit(st0);
+      const uint32_t d0 = atomicAdd(&s_sdone[ring_slot(k0)], (uint32_t)n0);
+      if (d0 + (uint32_t)n0 == (uint32_t)IU) finish_unit(ring_slot(k0));
       if (k1 != k0) {
         const int n1 = 32 - n0;
-        const uint32_t d1 = atomicAdd(&s_sdone[st1], (uint32_t)n1);
-        if (d1 + (uint32_t)n1 == (uint32_t)IU) finish_unit(st1);
+        const uint32_t d1 = atomicAdd(&s_sdone[ring_slot(k1)], (uint32_t)n1);
+        if (d1 + (uint32_t)n1 == (uint32_t)IU) finish_unit(ring_slot(k1));
       }
     }
     __syncwarp();
