@@ -31,8 +31,8 @@ tools/color_flow: tools/color_flow.cpp include/bbme.h $(LIB)
 oracle:
 	$(MAKE) -C oracle
 
-micro: bench_micro/int_peak
-bench_micro/int_peak: bench_micro/int_peak.cu
+micro: bench_micro/int_peak bench_micro/shift_pipe
+bench_micro/%: bench_micro/%.cu
 	$(NVCC) -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o $@ $<
 
 clean:

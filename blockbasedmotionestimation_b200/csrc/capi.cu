@@ -42,6 +42,7 @@ struct Slot {
   int16_t* stage[2] = {nullptr, nullptr};
   Ticket* ticket[2] = {nullptr, nullptr};
   int stage_turn = 0;
+  uint8_t* sh4[kMaxLevels] = {};  // image 2 of the level in four byte phases (search kernels with pre = 1), 4 planes per pair
   TmaSearchPlan tma[kMaxLevels];
   TmaSearchPlan tma_seq[kMaxLevels];  // sequence mode: image 2 of pair i is plane i + 1 of the image-1 array
   std::vector<cudaEvent_t> ev;
@@ -280,9 +281,13 @@ int run_chunk(bbme_ctx* c, Slot& s, int n, const uint8_t* d_in1, const uint8_t* 
       launch_copy_mvs(s.mv_final[l + 1], sh.level_width[l + 1] / 2, c->cap[l + 1], sh.block_size[l + 1], field, g, n, st);
       ++c->launches;
     }
-    mark(c, s, TAG_OTHER);
     const TmaSearchPlan& tplan = seq ? s.tma_seq[l] : s.tma[l];
     const bool use_tma = tplan.supported && c->opt.search_kernel != 1 && c->opt.search_variant == 0;
+    if (use_tma && tplan.pre) {  // the window image in its four byte phases (sequence mode: pair i's image 2 is frame i + 1)
+      launch_shift4(i2, s.sh4[l], n, st);
+      ++c->launches;
+    }
+    mark(c, s, TAG_OTHER);
     unsigned long long* ctrs = c->opt.collect_stats ? s.counters : nullptr;
     if (use_tma) {
       if (launch_search_tma(tplan, i1, i2, field, n, ctrs, c->sm_count, st) != 0)
@@ -644,11 +649,14 @@ int bbme_plan(bbme_ctx* c, int width, int height, int num_levels, const int* sea
       if (o.search_kernel == 1) continue;
       char msg[256] = {0};
       const int R = radius_of(sh.search_size[l], sh.block_size[l]);
-      int trc = tma_search_plan(&s.tma[l], s.img[0][l], s.img[1][l], sh.level_width[l], sh.level_height[l], c->pitch[l],
+      if (tma_search_wants_pre(sh.level_width[l], sh.level_height[l], sh.block_size[l], R) &&
+          (rc = dev_alloc(c, &s.sh4[l], n * 4 * c->plane[l], false)))
+        return rc;
+      int trc = tma_search_plan(&s.tma[l], s.img[0][l], s.img[1][l], s.sh4[l], sh.level_width[l], sh.level_height[l], c->pitch[l],
                                 c->plane[l], o.chunk_pairs, sh.block_size[l], R, msg, sizeof(msg));
       if (trc != 0) return fail(c, BBME_E_CUDA, "TMA search plan failed at level %d: %s", l, msg);
       if (trc == 0)
-        trc = tma_search_plan(&s.tma_seq[l], s.img[0][l], s.img[0][l] + c->plane[l], sh.level_width[l], sh.level_height[l],
+        trc = tma_search_plan(&s.tma_seq[l], s.img[0][l], s.img[0][l] + c->plane[l], s.sh4[l], sh.level_width[l], sh.level_height[l],
                               c->pitch[l], c->plane[l], o.chunk_pairs, sh.block_size[l], R, msg, sizeof(msg));
       if (trc != 0) return fail(c, BBME_E_CUDA, "TMA search plan (sequence mode) failed at level %d: %s", l, msg);
       if (o.search_kernel == 2 && !s.tma[l].supported)
@@ -1188,8 +1196,12 @@ int bbme_stage_search(bbme_ctx* c, const uint8_t* im1, const uint8_t* im2, int w
   memset(&plan, 0, sizeof(plan));
   if (kernel != 1) {
     char msg[256] = {0};
-    if (tma_search_plan(&plan, d1, d2, w, h, pitch, (size_t)pitch * h, 1, bs, R, msg, sizeof(msg)) != 0)
+    uint8_t* d2s = nullptr;  // the byte-shifted copies, where the planned path would use them too
+    if (tma_search_wants_pre(w, h, bs, R) && !(d2s = sc.get<uint8_t>((size_t)pitch * h * 4, false)))
+      return fail(c, BBME_E_NOMEM, "stage: cudaMalloc failed");
+    if (tma_search_plan(&plan, d1, d2, d2s, w, h, pitch, (size_t)pitch * h, 1, bs, R, msg, sizeof(msg)) != 0)
       return fail(c, BBME_E_CUDA, "stage_search: %s", msg);
+    if (plan.supported && plan.pre) launch_shift4(i2, d2s, 1, 0);
     if (kernel == 2 && !plan.supported) return fail(c, BBME_E_ARG, "stage_search: (block %d, R %d) not covered by the TMA kernel", bs, R);
   }
   cudaEvent_t e0, e1;

@@ -81,6 +81,7 @@ int measure_int_peak(int sm_count, double* absdiff_per_s, double* sm_mhz);
 // ---- TMA search kernel (search_tma.cu)
 struct TmaSearchPlan {
   int supported;      // 0 if this (bs, R, geometry) is not handled by the TMA kernel
+  int pre;            // 1: map_win is the 4-D map over the four byte-shifted copies of image 2 (launch_shift4 first)
   int bs, R;
   int seg;            // candidate rows per thread item
   int band_rows;      // candidate rows per staged band
@@ -89,12 +90,16 @@ struct TmaSearchPlan {
   int threads;
   int stages;
   size_t smem_bytes;
-  CUtensorMap map_win;   // image 2 of this level: dims (w, h, n)
+  CUtensorMap map_win;   // image 2 of this level: dims (w, h, n); pre: dims (w, 4 copies, h, n)
   CUtensorMap map_blk;   // image 1 of this level
 };
 // returns 0 on success; fills plan->supported
-int tma_search_plan(TmaSearchPlan* plan, const uint8_t* img1, const uint8_t* img2, int w, int h, int pitch,
-                    size_t plane, int n_planes, int bs, int R, char* err, size_t errlen);
+// img2_shift4: room for 4 * plane bytes per pair (the byte-shifted copies written by launch_shift4 before every search launch
+// of a plan with pre = 1), or nullptr to stay with the funnel-shift kernels; tma_search_wants_pre says whether it would be used.
+int tma_search_plan(TmaSearchPlan* plan, const uint8_t* img1, const uint8_t* img2, const uint8_t* img2_shift4, int w, int h,
+                    int pitch, size_t plane, int n_planes, int bs, int R, char* err, size_t errlen);
+int tma_search_wants_pre(int w, int h, int bs, int R);
+void launch_shift4(ImgView src, uint8_t* dst, int n, cudaStream_t s);
 int launch_search_tma(const TmaSearchPlan& plan, ImgView i1, ImgView i2, MvView mv, int n,
                        unsigned long long* counters, int sm_count, cudaStream_t s);
 

@@ -132,6 +132,13 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
 // inverse of spiral_rank: rank -> (dx, dy)
 __device__ __forceinline__ void spiral_unrank(uint32_t rank, int& dx, int& dy) {
   dx = 0;
@@ -146,7 +153,7 @@ __device__ __forceinline__ void spiral_unrank(uint32_t rank, int& dx, int& dy) {
   else { dy = -r; dx = (o - 6 * r) - r + 1; }
 }
 
-template <int BS, int SEG, int PWW, bool K64, bool DEEP>
+template <int BS, int SEG, int PWW, bool K64, bool DEEP, bool PRE>
 __global__ void __launch_bounds__(kThreads, kMinCtas)
 k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant__ CUtensorMap map_blk,
              const TmaSearchArgs a) {
@@ -154,6 +161,12 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
   constexpr int TWW = TW / 4;              // tile words per row
   constexpr int QN = BS / TW;              // tiles per block side
   constexpr int AP = BS >= 16 ? BS : 16;   // staged block row pitch (TMA inner extent is >= 16 bytes)
+  // PRE: the window image exists in four copies shifted by 0..3 bytes (k_shift4 below), staged by ONE 4-D tile load as
+  // [row][copy][PWW words]; a lane reads the copy of its column's byte phase and needs no funnel shift.  The byte alignment
+  // is 13 % of the ALU-pipe instructions of an item and only SHF/PRMT (ALU pipe) or IMAD.HI/IMAD.WIDE (which cost the same
+  // slot: bench_micro/shift_pipe.cu) can do it in the loop.  Copy stride PWW = 24 or 40 words puts the four byte phases of
+  // eight consecutive words into 32 different banks.
+  constexpr int RP = PRE ? 4 * PWW : PWW;  // words between consecutive window rows in a stage
 
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int SMAX = DEEP ? kMaxStages : kStages, BMAX = SMAX + 1;
@@ -238,10 +251,11 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
         s_meta[stage] = m;
         if (valid) {
           uint8_t* st = smem + (size_t)stage * a.stage_bytes;
-          mbar_arrive_expect_tx(&s_full[stage], (uint32_t)((a.box1_word ? 2 : 1) * a.box_bytes + a.blk_bytes));
+          mbar_arrive_expect_tx(&s_full[stage], (uint32_t)((PRE ? 4 : a.box1_word ? 2 : 1) * a.box_bytes + a.blk_bytes));
           const int wy = y2 - a.R + band * a.band_rows;
-          tma_load_3d(st, &map_win, &s_full[stage], wx_al, wy, pair);
-          if (a.box1_word) tma_load_3d(st + (size_t)a.box1_off_words * 4, &map_win, &s_full[stage], wx_al + 4 * a.box1_word, wy, pair);
+          if (PRE) tma_load_4d(st, &map_win, &s_full[stage], wx_al, 0, wy, pair);
+          else tma_load_3d(st, &map_win, &s_full[stage], wx_al, wy, pair);
+          if (!PRE && a.box1_word) tma_load_3d(st + (size_t)a.box1_off_words * 4, &map_win, &s_full[stage], wx_al + 4 * a.box1_word, wy, pair);
           tma_load_3d(st + a.win_bytes, &map_blk, &s_full[stage], (bx * BS) & ~15, by * BS, pair);
         } else {
           mbar_arrive(&s_full[stage]);
@@ -342,7 +356,7 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
       const int wi = bo >> 2;
       const int cy0 = sidx * SEG;
       const uint8_t* st = smem + (size_t)stage * a.stage_bytes;
-      const uint32_t* win = reinterpret_cast<const uint32_t*>(st) + cy0 * PWW;
+      const uint32_t* win = reinterpret_cast<const uint32_t*>(st) + cy0 * RP + (PRE ? (bo & 3) * PWW : 0);
       const uint8_t* blk = st + a.win_bytes + (BS == 8 ? ((m.x2 - m.predx) & 8) : 0);
 
       uint32_t acc[SEG];
@@ -366,14 +380,14 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
         }
         // word column of this lane's tile row start; with two boxes, take the one that holds words wq .. wq + TWW
         const int wq = wi + qx * TWW;
-        const uint32_t* wb = win + qy * TW * PWW + ((a.box1_word && wq > PWW - 1 - TWW) ? a.box1_off_words + wq - a.box1_word : wq);
+        const uint32_t* wb = win + qy * TW * RP + ((!PRE && a.box1_word && wq > PWW - 1 - TWW) ? a.box1_off_words + wq - a.box1_word : wq);
 #pragma unroll
         for (int jr = 0; jr < SEG + TW - 1; ++jr) {
           uint32_t raw[TWW + 1], wv[TWW];
 #pragma unroll
-          for (int kk = 0; kk <= TWW; ++kk) raw[kk] = wb[jr * PWW + kk];  // compile-time offsets: no address arithmetic
+          for (int kk = 0; kk < TWW + (PRE ? 0 : 1); ++kk) raw[kk] = wb[jr * RP + kk];  // compile-time offsets: no address arithmetic
 #pragma unroll
-          for (int kk = 0; kk < TWW; ++kk) wv[kk] = __funnelshift_r(raw[kk], raw[kk + 1], sh);
+          for (int kk = 0; kk < TWW; ++kk) wv[kk] = PRE ? raw[kk] : __funnelshift_r(raw[kk], raw[kk + 1], sh);
 #pragma unroll
           for (int kk = 0; kk < TWW; ++kk) {
 #pragma unroll
@@ -504,6 +518,48 @@ static int encode_u8_3d(CUtensorMap* map, const uint8_t* base, int w, int h, int
   return r == CUDA_SUCCESS ? 0 : -2;
 }
 
+// The four byte phases of the window image as one 4-D tensor: dims (x, copy, y, pair) over the [pair][y][copy][pitch] array
+// that k_shift4 writes; box = (box_w, 4, box_h, 1) lands in shared memory as [row][copy][box_w].
+static int encode_u8_4copies(CUtensorMap* map, const uint8_t* base, int w, int h, int pitch, size_t plane, int n, int box_w, int box_h) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return -1;
+  cuuint64_t dims[4] = {(cuuint64_t)w, 4u, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)pitch, (cuuint64_t)pitch * 4u, (cuuint64_t)plane * 4u};
+  cuuint32_t box[4] = {(cuuint32_t)box_w, 4u, (cuuint32_t)box_h, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+// dst[pair][y][c][x] = src[pair][y][x + c], c = 0..3 (bytes past the row's pitch read as 0): HBM-bound, 16 bytes in and
+// 64 bytes out per thread.  Columns >= w - c of copy c only ever feed candidates that leave the image, which are masked.
+__global__ void __launch_bounds__(128) k_shift4(const uint8_t* __restrict__ src, int pitch, size_t plane, int h, uint8_t* __restrict__ dst) {
+  const int x = (blockIdx.x * 128 + threadIdx.x) * 16;
+  if (x >= pitch) return;
+  const int y = blockIdx.y, pair = blockIdx.z;
+  const uint8_t* row = src + (size_t)pair * plane + (size_t)y * pitch;
+  const uint4 v = *reinterpret_cast<const uint4*>(row + x);
+  const uint32_t nx = x + 16 < pitch ? *reinterpret_cast<const uint32_t*>(row + x + 16) : 0u;
+  uint8_t* out = dst + ((size_t)pair * h + y) * 4 * (size_t)pitch + x;
+  *reinterpret_cast<uint4*>(out) = v;
+#pragma unroll
+  for (int c = 1; c < 4; ++c) {
+    uint4 o;
+    o.x = __funnelshift_r(v.x, v.y, 8 * c);
+    o.y = __funnelshift_r(v.y, v.z, 8 * c);
+    o.z = __funnelshift_r(v.z, v.w, 8 * c);
+    o.w = __funnelshift_r(v.w, nx, 8 * c);
+    *reinterpret_cast<uint4*>(out + (size_t)c * pitch) = o;
+  }
+}
+
+void launch_shift4(ImgView src, uint8_t* dst, int n, cudaStream_t s) {
+  dim3 grid((src.pitch / 16 + 127) / 128, src.h, n);
+  k_shift4<<<grid, 128, 0, s>>>(src.p, src.pitch, src.plane, src.h, dst);
+}
+
 static int pick_seg(int bs, int R) {
   // Candidate rows per lane.  Cost of a 32-lane work item per lane, in ALU-pipe instructions: the funnel shifts of
   // SEG + T - 1 window rows, SEG * T * T/4 SADs, ~2 per candidate for the key, and a fixed part (item fetch, tile
@@ -532,11 +588,15 @@ struct TmaGeom {
   int seg;
   int k64;
   int deep;  // the DEEP instantiation (ring of 8 or 16 stages) runs this geometry
+  int pre;   // the PRE instantiation (four byte-shifted copies of the window, no funnel shifts) runs this geometry
   int box_w, box_h;
   size_t smem;
 };
 
-static bool make_geom(int w, int h, int bs, int R, TmaGeom* g) {
+constexpr size_t kSmemCap = 200 * 1024;     // dynamic shared memory of a CTA
+constexpr size_t kSmemCapPre = 224 * 1024;  // PRE stages are four times as large: all an SM has (227 KB less the static variables)
+
+static bool make_geom_impl(int w, int h, int bs, int R, bool pre, TmaGeom* g) {
   if (!(bs == 8 || bs == 16 || bs == 32)) return false;
   if (R < 1) return false;
   memset(g, 0, sizeof(*g));
@@ -563,22 +623,24 @@ static bool make_geom(int w, int h, int bs, int R, TmaGeom* g) {
     two_box = 1;
   }
   const bool use_k64 = k64 || two_box;
+  if (pre && (use_k64 || (pww != 24 && pww != 40))) return false;  // copy stride = pitch: only these two spread the banks
+  const size_t cap = pre ? kSmemCapPre : kSmemCap;
   const int box_w = pww * 4;
   const int segs_total = (n + seg - 1) / seg;
   const int blk_bytes = bs * (bs >= 16 ? bs : 16);
   // per stage: 24 KB, or what the CTA's 200 KB leave per stage next to the spiral-rank table
   const size_t rank_bytes = use_k64 ? 0 : (((size_t)(n + seg) * n * 2 + 127) / 128) * 128;
-  size_t budget = (200 * 1024 - rank_bytes) / kStages / 128 * 128;
-  if (budget > 24 * 1024) budget = 24 * 1024;
+  size_t budget = (cap - rank_bytes) / kStages / 128 * 128;
+  if (!pre && budget > 24 * 1024) budget = 24 * 1024;
   int spb = segs_total;
   size_t one_box = 0;
   for (;;) {
     const int box_h = spb * seg + bs - 1;
     one_box = (((size_t)box_h * box_w) + 127) / 128 * 128;
-    const size_t win_bytes = one_box * (two_box ? 2 : 1);
+    const size_t win_bytes = pre ? (((size_t)box_h * box_w * 4) + 127) / 128 * 128 : one_box * (two_box ? 2 : 1);
     const size_t stage = win_bytes + ((blk_bytes + 127) / 128) * 128;
     if ((stage <= budget && box_h <= 256) || spb == 1) {
-      if (stage > 64 * 1024 || box_h > 256) return false;
+      if (stage > (pre ? budget : (size_t)64 * 1024) || box_h > 256) return false;
       g->box_h = box_h;
       g->a.win_bytes = (int)win_bytes;
       g->a.stage_bytes = (int)stage;
@@ -605,10 +667,11 @@ static bool make_geom(int w, int h, int bs, int R, TmaGeom* g) {
   // as deep a ring as the shared memory holds (the stage size above was chosen for kStages stages)
   {
     const size_t rank_b = use_k64 ? 0 : (((size_t)(n + seg) * n * 2 + 127) / 128) * 128;
-    int st = (int)((200 * 1024 - rank_b) / (size_t)g->a.stage_bytes);
+    int st = (int)((cap - rank_b) / (size_t)g->a.stage_bytes);
     // sixteen consumer warps want ~16 work items ready: a deep ring where a unit holds few items (32x32 / +-16: three), the
     // kStages that the large-window geometries were tuned with elsewhere (config 2 measured the same at 5, 8 and 16)
     const int items_per_unit = (n * spb + 31) / 32;
+    if (pre && items_per_unit * kStages < 32 && st < 8) return false;          // few items per unit want the deep ring more than the copies
     if (items_per_unit * kStages >= 32 || use_k64 || pww > 32) st = kStages;  // DEEP instantiations exist for pitch classes <= 32
     if (const char* e = getenv("BBME_SEARCH_STAGES")) st = atoi(e);             // tuning runs
     g->deep = (st >= 8 && !use_k64 && pww <= 32) ? 1 : 0;
@@ -617,58 +680,84 @@ static bool make_geom(int w, int h, int bs, int R, TmaGeom* g) {
   }
   g->a.rank_off = g->a.stages * g->a.stage_bytes;
   g->smem = (size_t)g->a.rank_off + (use_k64 ? 0 : (((size_t)(n + seg) * n * 2 + 127) / 128) * 128);
-  if (g->smem > 200 * 1024) return false;  // ring + rank table must fit the CTA's shared memory: generic kernel instead
+  if (g->smem > cap) return false;  // ring + rank table must fit the CTA's shared memory: generic kernel instead
+  g->pre = pre ? 1 : 0;
   return true;
 }
 
+static bool pre_enabled() {
+  const char* e = getenv("BBME_SEARCH_PRE");  // tuning / A-B runs: 0 keeps the funnel-shift kernels
+  return !(e && atoi(e) == 0);
+}
+
+static bool make_geom(int w, int h, int bs, int R, bool want_pre, TmaGeom* g) {
+  if (want_pre && pre_enabled() && make_geom_impl(w, h, bs, R, true, g)) return true;
+  return make_geom_impl(w, h, bs, R, false, g);
+}
+
+int tma_search_wants_pre(int w, int h, int bs, int R) {
+  TmaGeom g;
+  return make_geom(w, h, bs, R, true, &g) && g.pre;
+}
+
 // One instantiation: a == nullptr prepares it (shared-memory opt-in, once per plan), else launches it.
-template <int BS, int SEG, int PWW, bool K64, bool DEEP>
+template <int BS, int SEG, int PWW, bool K64, bool DEEP, bool PRE>
 static int run_inst(const TmaSearchPlan& plan, const TmaSearchArgs* a, int grid, cudaStream_t s) {
   if (!a)
-    return cudaFuncSetAttribute(k_search_tma<BS, SEG, PWW, K64, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess ? 1 : -1;
-  k_search_tma<BS, SEG, PWW, K64, DEEP><<<grid, kThreads, plan.smem_bytes, s>>>(plan.map_win, plan.map_blk, *a);
+    return cudaFuncSetAttribute(k_search_tma<BS, SEG, PWW, K64, DEEP, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(PRE ? kSmemCapPre : kSmemCap)) == cudaSuccess ? 1 : -1;
+  k_search_tma<BS, SEG, PWW, K64, DEEP, PRE><<<grid, kThreads, plan.smem_bytes, s>>>(plan.map_win, plan.map_blk, *a);
   return 1;
 }
 
 // Finds the instantiation of (block size, rows per lane, window pitch class, key width).  Returns 1 = done, 0 = there is none
 // (the caller falls back to the generic kernel at plan time; never silently at launch time), -1 = CUDA error.
 static int dispatch(const TmaSearchPlan& plan, int k64, int pww, int deep, const TmaSearchArgs* a, int grid, cudaStream_t s) {
+  const int pre = plan.pre;
 #define BBME_CASE(BS_, SEG_, PWW_) \
-  if (!k64 && !deep && plan.bs == BS_ && plan.seg == SEG_ && pww == PWW_) return run_inst<BS_, SEG_, PWW_, false, false>(plan, a, grid, s);
+  if (!k64 && !deep && !pre && plan.bs == BS_ && plan.seg == SEG_ && pww == PWW_) return run_inst<BS_, SEG_, PWW_, false, false, false>(plan, a, grid, s);
 #define BBME_CASED(BS_, SEG_, PWW_) /* small windows also exist with the deep ring */ \
   BBME_CASE(BS_, SEG_, PWW_) \
-  if (!k64 && deep && plan.bs == BS_ && plan.seg == SEG_ && pww == PWW_) return run_inst<BS_, SEG_, PWW_, false, true>(plan, a, grid, s);
+  if (!k64 && deep && !pre && plan.bs == BS_ && plan.seg == SEG_ && pww == PWW_) return run_inst<BS_, SEG_, PWW_, false, true, false>(plan, a, grid, s);
+#define BBME_CASEP(BS_, SEG_, PWW_, DEEP_) /* pitch classes 24 and 40 also exist over byte-shifted copies */ \
+  if (!k64 && deep == DEEP_ && pre && plan.bs == BS_ && plan.seg == SEG_ && pww == PWW_) return run_inst<BS_, SEG_, PWW_, false, DEEP_ != 0, true>(plan, a, grid, s);
 #define BBME_CASE64(BS_, SEG_, PWW_) \
-  if (k64 && plan.bs == BS_ && plan.seg == SEG_ && pww == PWW_) return run_inst<BS_, SEG_, PWW_, true, false>(plan, a, grid, s);
+  if (k64 && plan.bs == BS_ && plan.seg == SEG_ && pww == PWW_) return run_inst<BS_, SEG_, PWW_, true, false, false>(plan, a, grid, s);
 #define BBME_CASES(BS_, SEG_) \
   BBME_CASED(BS_, SEG_, 16) BBME_CASED(BS_, SEG_, 24) BBME_CASED(BS_, SEG_, 32) BBME_CASE(BS_, SEG_, 40) \
-  BBME_CASE(BS_, SEG_, 48) BBME_CASE(BS_, SEG_, 64)
+  BBME_CASE(BS_, SEG_, 48) BBME_CASE(BS_, SEG_, 64) \
+  BBME_CASEP(BS_, SEG_, 24, 0) BBME_CASEP(BS_, SEG_, 24, 1) BBME_CASEP(BS_, SEG_, 40, 0)
   BBME_CASES(8, 13) BBME_CASES(8, 11) BBME_CASES(8, 26) BBME_CASES(8, 43) BBME_CASES(16, 13) BBME_CASES(16, 11) BBME_CASES(32, 13) BBME_CASES(32, 11)
   BBME_CASE64(16, 13, 40) BBME_CASE64(16, 13, 64) BBME_CASE64(16, 11, 40) BBME_CASE64(16, 11, 64)
   BBME_CASE64(32, 13, 40) BBME_CASE64(32, 13, 64) BBME_CASE64(32, 11, 40) BBME_CASE64(32, 11, 64)
 #undef BBME_CASE64
+#undef BBME_CASEP
 #undef BBME_CASES
 #undef BBME_CASED
 #undef BBME_CASE
   return 0;
 }
 
-int tma_search_plan(TmaSearchPlan* plan, const uint8_t* img1, const uint8_t* img2, int w, int h, int pitch,
-                    size_t plane, int n_planes, int bs, int R, char* err, size_t errlen) {
+int tma_search_plan(TmaSearchPlan* plan, const uint8_t* img1, const uint8_t* img2, const uint8_t* img2_shift4, int w, int h,
+                    int pitch, size_t plane, int n_planes, int bs, int R, char* err, size_t errlen) {
   memset(plan, 0, sizeof(*plan));
   TmaGeom g;
-  if (!make_geom(w, h, bs, R, &g)) return 0;  // not supported: caller uses the generic kernel
+  bool want_pre = img2_shift4 != nullptr;
+again:
+  if (!make_geom(w, h, bs, R, want_pre, &g)) return 0;  // not supported: caller uses the generic kernel
   if (!get_encode()) {
     if (err) snprintf(err, errlen, "cuTensorMapEncodeTiled entry point not available");
     return -1;
   }
-  if (encode_u8_3d(&plan->map_win, img2, w, h, pitch, plane, n_planes, g.box_w, g.box_h) != 0 ||
+  if ((g.pre ? encode_u8_4copies(&plan->map_win, img2_shift4, w, h, pitch, plane, n_planes, g.box_w, g.box_h)
+             : encode_u8_3d(&plan->map_win, img2, w, h, pitch, plane, n_planes, g.box_w, g.box_h)) != 0 ||
       encode_u8_3d(&plan->map_blk, img1, w, h, pitch, plane, n_planes, bs >= 16 ? bs : 16, bs) != 0) {
     if (err) snprintf(err, errlen, "cuTensorMapEncodeTiled failed (w=%d h=%d pitch=%d box=%dx%d)", w, h, pitch, g.box_w, g.box_h);
     return -1;
   }
   plan->bs = bs;
   plan->R = R;
+  plan->pre = g.pre;
   plan->seg = g.seg;
   plan->band_rows = g.a.band_rows;
   plan->box_w = g.box_w;
@@ -679,6 +768,10 @@ int tma_search_plan(TmaSearchPlan* plan, const uint8_t* img1, const uint8_t* img
   plan->smem_bytes = g.smem;
   // the kernel for this geometry must exist NOW: a geometry without an instantiation runs the generic kernel
   const int have = dispatch(*plan, g.k64, g.a.pww, g.deep, nullptr, 0, nullptr);
+  if (have == 0 && g.pre) {  // no PRE instantiation for this (block, rows per lane, pitch): the funnel-shift kernel of the geometry
+    want_pre = false;
+    goto again;
+  }
   if (have < 0) {
     if (err) snprintf(err, errlen, "cudaFuncSetAttribute(max dynamic shared memory) failed for the search kernel");
     return -1;
@@ -691,7 +784,7 @@ int launch_search_tma(const TmaSearchPlan& plan, ImgView i1, ImgView i2, MvView 
                       unsigned long long* counters, int sm_count, cudaStream_t s) {
   (void)i2;
   TmaGeom g;
-  if (!plan.supported || !make_geom(i1.w, i1.h, plan.bs, plan.R, &g)) return -1;
+  if (!plan.supported || !make_geom(i1.w, i1.h, plan.bs, plan.R, plan.pre != 0, &g) || g.pre != plan.pre) return -1;
   TmaSearchArgs a = g.a;
   a.n_pairs = n;
   a.mv = mv.p;
