@@ -69,6 +69,8 @@ struct TmaSearchArgs {
   int box1_word;       // 0: one window box; else the word column where the second (overlapping) box starts
   int box1_off_words;  // word offset of the second box inside a stage
   int stage_shift;     // log2(stages) when stages is a power of two, 0 when stages == kStages
+  uint32_t n_magic;    // floor(2^32 / n) + 1: q / n == umulhi(q, n_magic) while q * n < 2^32 (0: divide)
+  uint32_t iu_magic;   // the same for the lanes per unit (0: divide)
   int stages;          // ring depth of this launch (kStages .. kMaxStages): small units (32x32 blocks with +-16: three work items
                        // per unit) need a deep ring to keep sixteen consumer warps fed, large windows only fit a shallow one
   short2* mv;
@@ -110,6 +112,10 @@ __device__ __forceinline__ void mbar_stuck(int who, int k, uint32_t parity) {
 #endif
   __trap();
 }
+// SLEEP_NS > 0: back off between polls.  The producer's ring is full nearly all the time; polled back to back its wait loop
+// was 5 % of the kernel's executed instructions and took issue slots and ALU-pipe slots (VIADD, ISETP) from the consumer warps
+// of its sub-partition (profiles/r02_search_l0_ncu.txt).
+template <int SLEEP_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int who = 0, int k = 0) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok = 0;
@@ -122,7 +128,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int wh
         : "=r"(ok)
         : "r"(addr), "r"(parity)
         : "memory");
-    if (!ok && ++polls > (1u << 24)) mbar_stuck(who, k, parity);
+    if (!ok) {
+      if (++polls > (1u << (SLEEP_NS ? 22 : 24))) mbar_stuck(who, k, parity);
+      if (SLEEP_NS) __nanosleep(SLEEP_NS);
+    }
   }
 }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
@@ -227,7 +236,7 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
     if (lane == 0) {
       for (int k = 0; k < my_units; ++k) {
         const int stage = ring_slot(k);
-        if (k >= NS) mbar_wait(&s_empty[stage], (uint32_t)(ring_turn(k) - 1) & 1u, 1, k);
+        if (k >= NS) mbar_wait<400>(&s_empty[stage], (uint32_t)(ring_turn(k) - 1) & 1u, 1, k);
         const int lb = k / a.nbands, band = k - lb * a.nbands;
         if (band == 0) {
           // units complete out of order, so the block that used this key slot NB blocks ago may still be in
@@ -329,7 +338,7 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
     t = __shfl_sync(0xffffffffu, t, 0);
     const int T0 = (int)t * 32;
     if (T0 >= total_lanes) break;
-    const int k0 = T0 / IU;                              // unit of lane 0
+    const int k0 = a.iu_magic ? (int)__umulhi((uint32_t)T0, a.iu_magic) : T0 / IU;  // unit of lane 0
     const int split = (k0 + 1) * IU - T0;                // lanes [0, split) belong to k0, the rest to k0 + 1
     const int k1 = (split < 32 && k0 + 1 < my_units) ? k0 + 1 : k0;
     wait_unit(k0);
@@ -342,10 +351,9 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
     const StageMeta m = s_meta[stage];
     const int q = T - kl * IU;
     const int segs_here = min(a.segs_per_band, a.segs_total - m.band * a.segs_per_band);
-    const int sidx_raw = q / a.n;
+    const int sidx_raw = a.n_magic ? (int)__umulhi((uint32_t)q, a.n_magic) : q / a.n;  // q >= 0
     const bool active = T < total_lanes && (!second || k1 != k0) && m.valid && sidx_raw < segs_here;
-    const int qq = active ? q : 0;
-    const int sidx = qq / a.n, o = qq - sidx * a.n;
+    const int sidx = active ? sidx_raw : 0, o = active ? q - sidx_raw * a.n : 0;
     uint32_t best = 0xffffffffu, best_rank = 0xffffffffu;  // K64: best = SAD, best_rank = its spiral rank
     uint32_t eqmask = 0;   // K64: the lane's candidates that attain `best`
     int rank_dx = 0, rank_dy0 = 0;
@@ -671,7 +679,7 @@ static bool make_geom_impl(int w, int h, int bs, int R, bool pre, TmaGeom* g) {
     // sixteen consumer warps want ~16 work items ready: a deep ring where a unit holds few items (32x32 / +-16: three), the
     // kStages that the large-window geometries were tuned with elsewhere (config 2 measured the same at 5, 8 and 16)
     const int items_per_unit = (n * spb + 31) / 32;
-    if (pre && items_per_unit * kStages < 32 && st < 8) return false;          // few items per unit want the deep ring more than the copies
+    if (pre && items_per_unit * kStages < 32 && st < 8 && !getenv("BBME_SEARCH_PRE_FORCE")) return false;  // few items per unit want the deep ring more than the copies
     if (items_per_unit * kStages >= 32 || use_k64 || pww > 32) st = kStages;  // DEEP instantiations exist for pitch classes <= 32
     if (const char* e = getenv("BBME_SEARCH_STAGES")) st = atoi(e);             // tuning runs
     g->deep = (st >= 8 && !use_k64 && pww <= 32) ? 1 : 0;
@@ -793,6 +801,13 @@ int launch_search_tma(const TmaSearchPlan& plan, ImgView i1, ImgView i2, MvView 
   const int total = a.gw * a.gh * n;
   int grid = sm_count * kMinCtas;
   if (grid > total) grid = total;
+  {
+    // exact multiply-high division (three integer divisions per 32-lane item otherwise): valid while dividend * divisor < 2^32
+    const unsigned long long iu = (unsigned long long)(a.n * a.segs_per_band > 32 ? a.n * a.segs_per_band : 32);
+    const unsigned long long units_per_cta = ((unsigned long long)total + grid - 1) / grid * a.nbands;
+    a.n_magic = (iu + 64) * (unsigned long long)a.n < (1ull << 32) ? (uint32_t)((1ull << 32) / (unsigned)a.n + 1) : 0u;
+    a.iu_magic = (units_per_cta * iu + 64) * iu < (1ull << 32) ? (uint32_t)((1ull << 32) / iu + 1) : 0u;
+  }
   return dispatch(plan, g.k64, a.pww, g.deep, &a, grid, s) == 1 ? 0 : -1;
 }
 

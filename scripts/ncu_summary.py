@@ -24,3 +24,36 @@ for r in rows[2:]:
     st = sorted(((float(v), k[len(STALL):].replace('_per_issue_active.ratio', '')) for k, v in d.items() if k.startswith(STALL) and v not in ("", "n/a")), reverse=True)
     print("stall reasons (warps per issue-active cycle):", ", ".join(f"{n}={v:.2f}" for v, n in st[:9]))
     print()
+
+# ---- dynamic instruction mix (source page, needs --import-source on / SASS): executed warp instructions per opcode, and the
+# share of the ALU-pipe opcodes that is VABSDIFF4 (what separates the ALU pipe's utilisation from the roofline fraction)
+ALU_PIPE = {"VABSDIFF4", "SHF", "PRMT", "LOP3", "IADD3", "VIADD", "ISETP", "VIMNMX", "VIMNMX3", "LEA", "SEL", "IABS", "IMNMX", "FMNMX",
+            "PLOP3", "FSETP", "SGXT", "BMSK", "FLO", "POPC", "MOV", "CS2R", "IADD", "FSEL", "VOTE", "P2R", "R2P"}
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+hist, name = {}, None
+def flush():
+    if not hist:
+        return
+    tot = sum(hist.values())
+    alu = sum(v for k, v in hist.items() if k in ALU_PIPE)
+    print(f"dynamic instruction mix of {name}: {tot} warp instructions")
+    print("  " + ", ".join(f"{k} {v / tot * 100:.1f}%" for k, v in sorted(hist.items(), key=lambda kv: -kv[1])[:14]))
+    if hist.get("VABSDIFF4"):
+        print(f"  ALU-pipe opcodes {alu / tot * 100:.1f}% of all; VABSDIFF4 {hist['VABSDIFF4'] / alu * 100:.1f}% of the ALU-pipe opcodes")
+    print()
+col = None
+for r in csv.reader(io.StringIO(src)):
+    if len(r) >= 2 and r[0] == "Kernel Name":
+        flush(); hist, name, col = {}, r[1], None
+    elif len(r) > 5 and r[0] == "Address":
+        col = (r.index("Source"), r.index("Instructions Executed"))
+    elif col and len(r) > max(col) and r[0].startswith("0x"):
+        toks = r[col[0]].split()
+        if toks and toks[0].startswith("@"):
+            toks = toks[1:]
+        if toks:
+            try:
+                hist[toks[0].split(".")[0].rstrip(";")] = hist.get(toks[0].split(".")[0].rstrip(";"), 0) + int(r[col[1]])
+            except ValueError:
+                pass
+flush()
