@@ -568,16 +568,21 @@ void launch_shift4(ImgView src, uint8_t* dst, int n, cudaStream_t s) {
   k_shift4<<<grid, 128, 0, s>>>(src.p, src.pitch, src.plane, src.h, dst);
 }
 
-static int pick_seg(int bs, int R) {
+static int pick_seg(int bs, int R, bool pre) {
   // Candidate rows per lane.  Cost of a 32-lane work item per lane, in ALU-pipe instructions: the funnel shifts of
   // SEG + T - 1 window rows, SEG * T * T/4 SADs, ~2 per candidate for the key, and a fixed part (item fetch, tile
   // load, reductions) that weighs most on 8x8 blocks, whose items hold a quarter of the SADs of a 16x16 item.
-  // 16x16 / 32x32: 13 or 11 (17 and 22 were measured slower, with and without register spills); 8x8 blocks also get
+  // 16x16 / 32x32: 13 or 11 (17 and 22 were measured slower, with and without register spills -- 22 again in round 2 over the
+  // byte-shifted copies with 15 consumer warps and 119 registers: 76 % against 83 % of the integer peak); 8x8 blocks also get
   // 26 and 43: config 3 (8x8, +-64) went from 42 % to 64 % of the integer peak with 43.
   const int n = 2 * R + 1;
   const int T = bs >= 16 ? 16 : bs;
   const int cands[4] = {13, 11, 26, 43};
   const int ncand = bs == 8 ? 4 : 2;
+  if (const char* e = getenv("BBME_SEARCH_SEG")) {  // tuning runs
+    const int v = atoi(e);
+    if (v == 13 || v == 11 || (bs == 8 && (v == 26 || v == 43))) return v;
+  }
   int best = 13;
   double best_eff = -1.0;
   for (int i = 0; i < ncand; ++i) {
@@ -613,7 +618,7 @@ static bool make_geom_impl(int w, int h, int bs, int R, bool pre, TmaGeom* g) {
   const bool k64 = n * n > (bs >= 32 ? (1 << 14) : (1 << 16)) - 1;
   if (k64 && bs == 8) return false;
   if ((long long)n * n > 0x7fffffffLL) return false;
-  const int seg = pick_seg(bs, R);
+  const int seg = pick_seg(bs, R, pre);
   // staged box: starts at the 16-byte aligned column at or below (x2 - R); a lane reads words
   // (off + o) >> 2 ... + bs/4 inclusive, with off <= 15 and o <= 2R
   const int words = ((15 + 2 * R) >> 2) + bs / 4 + 1;

@@ -15,7 +15,7 @@ timeout 600 ncu --set full --import-source on --clock-control none --kernel-name
 # regularisation: the level-1 and level-0 launches of the timed step (6 launches in the run)
 timeout 900 ncu --set full --import-source on --clock-control none --kernel-name regex:k_reg_level --launch-skip 4 --launch-count 2 -o $O/reg_level $B > $O/ncu_reg.log 2>&1; summ reg_level
 # HBM-bound kernels of the timed step
-timeout 600 ncu --set full --clock-control none --kernel-name regex:"k_(export|pyrdown|pad|copy_mvs)" --launch-skip 6 --launch-count 6 -o $O/hbm $B > $O/ncu_hbm.log 2>&1; summ hbm
+timeout 600 ncu --set full --clock-control none --kernel-name regex:"k_(export|pyrdown|pad|copy_mvs|shift4)" --launch-skip 9 --launch-count 9 -o $O/hbm $B > $O/ncu_hbm.log 2>&1; summ hbm
 BBME_REG_PROFILE=1 timeout 300 python scripts/reg_profile.py 128 1 > $O/regprof128.json 2> $O/regprof128.err
 BBME_REG_PROFILE=1 timeout 300 python scripts/reg_profile.py 1 8 > $O/regprof1.json 2> $O/regprof1.err
 timeout 120 python scripts/quarterpel_wrapper.py > $O/quarterpel.json 2> $O/quarterpel.err
