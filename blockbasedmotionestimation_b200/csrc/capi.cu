@@ -602,7 +602,7 @@ int bbme_plan(bbme_ctx* c, int width, int height, int num_levels, const int* sea
   bbme_options o;
   bbme_default_options(&o);
   if (opt) o = *opt;
-  if (o.sweeps < 0 || o.chunk_pairs < 1 || o.slots < 1 || o.slots > 4 || o.search_kernel < 0 || o.search_kernel > 2 ||
+  if (o.sweeps < 0 || o.chunk_pairs < 1 || o.slots < 1 || o.slots > 8 || o.search_kernel < 0 || o.search_kernel > 2 ||
       o.search_variant < 0 || o.search_variant > 1 || (o.search_variant == 1 && o.search_kernel == 2))
     return fail(c, BBME_E_ARG, "bbme_plan: bad options (sweeps=%d chunk_pairs=%d slots=%d search_kernel=%d search_variant=%d)",
                 o.sweeps, o.chunk_pairs, o.slots, o.search_kernel, o.search_variant);

@@ -77,7 +77,7 @@ typedef struct {
 typedef struct {
   int sweeps;          /* regularisation sweeps per block size; reference hard-codes 2 (motion_framework.cpp:143,184) */
   int chunk_pairs;     /* pairs resident on the device per pipeline slot (>=1) */
-  int slots;           /* pipeline slots (1..4); >1 overlaps H2D / compute / D2H of successive chunks */
+  int slots;           /* pipeline slots (1..8); >1 overlaps H2D / compute / D2H of successive chunks */
   int search_kernel;   /* 0 = auto, 1 = force the generic kernel, 2 = force the TMA kernel (error if unsupported) */
   int collect_stats;   /* 1 = per-stage CUDA-event timing + work counters (adds synchronisation) */
   int keep_search_mv;  /* 1 = keep a copy of every level's field after the search (for bbme_debug_level_mv) */

@@ -4,7 +4,7 @@
 # regularisation.  Reports are summarised on the box (scripts/ncu_summary.py); gpurun_out/ may not exceed 64 MiB.
 set -u
 O=gpurun_out/prof_r02; mkdir -p $O
-B="python bench.py --pairs 128 --chunk 128 --steps 1 --warmup 1 --no-cpu --no-check --no-e2e --no-other"
+B="python bench.py --pairs 128 --chunk 128 --slots 1 --steps 1 --warmup 1 --no-cpu --no-check --no-e2e --no-other"
 summ() { python scripts/ncu_summary.py $O/$1.ncu-rep > $O/$1.txt 2>&1; rm -f $O/$1.ncu-rep; }
 timeout 600 python bench.py --steps 20 --warmup 5 > $O/bench_n1.json 2> $O/bench_n1.err
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_ref.json 2> $O/bench_ref.err
