@@ -481,9 +481,10 @@ def run_ours(args, rank, local_rank, world):
         "algorithmic_absdiffs_per_launch": absdiffs / n_search,
         "avg_launch_ms": ms_search / n_search, "launches_per_step": n_search,
         "traffic": None,
-        "traffic_from_profile": {"bytes": 566.6e6, "file": "profiles/r01c_search_l0_ncu.txt",
+        "traffic_from_profile": {"bytes": 1398.4e6, "file": "profiles/r02_search_l0_ncu.txt",
                                  "note": "dram read+write of the level-0 launch of a 128-pair chunk from a committed ncu --set full "
-                                         "capture, NOT measured in this run; algorithmic 535 MB of frames + 4 MB of vectors"},
+                                         "capture, NOT measured in this run; algorithmic 1 331 MB: image 1 (266 MB), image 2 in its four "
+                                         "byte-shifted copies (1 061 MB, written by k_shift4 just before), 4 MB of vectors"},
     }
     roofline_hbm = {
         "bound": "hbm", "algorithmic_bytes_per_pair": alg_bytes_pair,

@@ -42,6 +42,7 @@ struct Slot {
   int16_t* stage[2] = {nullptr, nullptr};
   Ticket* ticket[2] = {nullptr, nullptr};
   int stage_turn = 0;
+  unsigned int* work_ctr = nullptr;  // block counter of the search launches (one word per level)
   uint8_t* sh4[kMaxLevels] = {};  // image 2 of the level in four byte phases (search kernels with pre = 1), 4 planes per pair
   TmaSearchPlan tma[kMaxLevels];
   TmaSearchPlan tma_seq[kMaxLevels];  // sequence mode: image 2 of pair i is plane i + 1 of the image-1 array
@@ -290,7 +291,7 @@ int run_chunk(bbme_ctx* c, Slot& s, int n, const uint8_t* d_in1, const uint8_t* 
     mark(c, s, TAG_OTHER);
     unsigned long long* ctrs = c->opt.collect_stats ? s.counters : nullptr;
     if (use_tma) {
-      if (launch_search_tma(tplan, i1, i2, field, n, ctrs, c->sm_count, st) != 0)
+      if (launch_search_tma(tplan, i1, i2, field, n, ctrs, s.work_ctr + l, c->sm_count, st) != 0)
         return fail(c, BBME_E_CUDA, "level %d: no TMA search kernel for block %d, R %d (plan and launch disagree)", l, g, R);
     } else {
       launch_search_generic(i1, i2, field, g, R, n, ctrs, st, c->opt.search_variant);
@@ -640,7 +641,7 @@ int bbme_plan(bbme_ctx* c, int width, int height, int num_levels, const int* sea
     if ((rc = dev_alloc(c, &s.list0, n * c->cap[0], false)) || (rc = dev_alloc(c, &s.list1, n * c->cap[0], false)) ||
         (rc = dev_alloc(c, &s.nv, n * c->cap[0], false)) || (rc = dev_alloc(c, &s.stamp, n * c->cap[0], true)) ||
         (rc = dev_alloc(c, &s.ctr, n * kCtrWords, true)) || (rc = dev_alloc(c, &s.counters, (size_t)2, true)) ||
-        (rc = dev_alloc(c, &s.out, n * (c->out_plane / 4 + 64), false)))
+        (rc = dev_alloc(c, &s.out, n * (c->out_plane / 4 + 64), false)) || (rc = dev_alloc(c, &s.work_ctr, (size_t)kMaxLevels, true)))
       return rc;
     if (getenv("BBME_REG_PROFILE") && (rc = dev_alloc(c, &s.hist, (size_t)kHistSweeps * 64, true))) return rc;
     for (int l = 0; l < L; ++l) {
@@ -1204,12 +1205,14 @@ int bbme_stage_search(bbme_ctx* c, const uint8_t* im1, const uint8_t* im2, int w
     if (plan.supported && plan.pre) launch_shift4(i2, d2s, 1, 0);
     if (kernel == 2 && !plan.supported) return fail(c, BBME_E_ARG, "stage_search: (block %d, R %d) not covered by the TMA kernel", bs, R);
   }
+  unsigned int* wc = sc.get<unsigned int>(1, true);
+  if (!wc) return fail(c, BBME_E_NOMEM, "stage: cudaMalloc failed");
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
   cudaEventRecord(e0, 0);
   if (plan.supported) {
-    if (launch_search_tma(plan, i1, i2, f, 1, ctr, c->sm_count, 0) != 0) return fail(c, BBME_E_CUDA, "stage_search: TMA kernel launch failed");
+    if (launch_search_tma(plan, i1, i2, f, 1, ctr, wc, c->sm_count, 0) != 0) return fail(c, BBME_E_CUDA, "stage_search: TMA kernel launch failed");
   } else {
     launch_search_generic(i1, i2, f, bs, R, 1, ctr, 0);
   }

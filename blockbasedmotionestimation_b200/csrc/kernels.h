@@ -100,7 +100,8 @@ int tma_search_plan(TmaSearchPlan* plan, const uint8_t* img1, const uint8_t* img
                     int pitch, size_t plane, int n_planes, int bs, int R, char* err, size_t errlen);
 int tma_search_wants_pre(int w, int h, int bs, int R);
 void launch_shift4(ImgView src, uint8_t* dst, int n, cudaStream_t s);
+// work_ctr: one device word owned by the caller's stream (zeroed here, then the kernel's block counter); nullptr = blocks strided by CTA
 int launch_search_tma(const TmaSearchPlan& plan, ImgView i1, ImgView i2, MvView mv, int n,
-                       unsigned long long* counters, int sm_count, cudaStream_t s);
+                       unsigned long long* counters, unsigned int* work_ctr, int sm_count, cudaStream_t s);
 
 }  // namespace bbme

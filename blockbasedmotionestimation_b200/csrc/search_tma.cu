@@ -69,8 +69,9 @@ struct TmaSearchArgs {
   int box1_word;       // 0: one window box; else the word column where the second (overlapping) box starts
   int box1_off_words;  // word offset of the second box inside a stage
   int stage_shift;     // log2(stages) when stages is a power of two, 0 when stages == kStages
-  uint32_t n_magic;    // floor(2^32 / n) + 1: q / n == umulhi(q, n_magic) while q * n < 2^32 (0: divide)
-  uint32_t iu_magic;   // the same for the lanes per unit (0: divide)
+  uint32_t n_magic, n_shift;    // x / n == umulhi(x, n_magic) >> n_shift for 0 <= x < 2^31 (magic 0: divide)
+  uint32_t iu_magic, iu_shift;  // the same for the lanes per unit
+  unsigned int* work_ctr;       // zeroed before the launch: the next block to hand out (nullptr: blocks strided by CTA index)
   int stages;          // ring depth of this launch (kStages .. kMaxStages): small units (32x32 blocks with +-16: three work items
                        // per unit) need a deep ring to keep sixteen consumer warps fed, large windows only fit a shallow one
   short2* mv;
@@ -134,6 +135,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int wh
     }
   }
 }
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {  // one poll
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -195,13 +207,12 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
   auto ring_slot = [&](int k) -> int { return DEEP ? (k & (NS - 1)) : (k % kStages); };
   auto ring_turn = [&](int k) -> int { return DEEP ? (k >> nshift) : (k / kStages); };
   __shared__ uint32_t s_next;
+  __shared__ int s_end;  // number of units this CTA stages, published by the producer after the last one (INT_MAX before)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblocks = a.gw * a.gh;
   const int total_blocks = nblocks * a.n_pairs;
   const int G = gridDim.x, cta = blockIdx.x;
-  const int my_blocks = cta < total_blocks ? (total_blocks - cta + G - 1) / G : 0;
-  const int my_units = my_blocks * a.nbands;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < SMAX; ++i) {
@@ -217,6 +228,7 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
       s_bbusy[i] = 0;
     }
     s_next = 0;
+    s_end = 0x7fffffff;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -234,10 +246,39 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
     if (lane == 0) {
-      for (int k = 0; k < my_units; ++k) {
+      // Blocks are handed out by a grid-wide counter: a CTA that starts late -- its SM was still running another stream's
+      // kernel, the normal case with several chunks in flight -- takes fewer blocks instead of holding the launch open for a
+      // fixed share (128 pairs as 4 x 32 on four streams: 4 360 -> 4 420 pairs/s).
+      const bool dyn = a.work_ctr != nullptr;
+      // two blocks ahead for the counter, one ahead for the block's predicted vector: both latencies (an L2 round trip each)
+      // stay off the staging path -- with 32x32 blocks and +-16 a block is consumed in ~3 us
+      auto fetch = [&](int prev) -> int { return dyn ? (int)atomicAdd(a.work_ctr, 1u) : prev + G; };
+      auto load_pred = [&](int g) -> short2 {
+        if (g >= total_blocks) return make_short2(0, 0);
+        const int pr = g / nblocks;
+        return a.mv[(size_t)pr * a.mv_plane + (g - pr * nblocks)];
+      };
+      int g0 = dyn ? fetch(0) : cta;
+      int g1 = fetch(g0);
+      short2 p0 = load_pred(g0);
+      short2 pred = make_short2(0, 0);
+      int gblk = 0, lb = -1, band = a.nbands - 1;
+      for (int k = 0;; ++k) {
+        if (++band == a.nbands) {  // next block
+          band = 0;
+          ++lb;
+          gblk = g0;
+          pred = p0;
+          if (gblk >= total_blocks) {
+            *reinterpret_cast<volatile int*>(&s_end) = k;
+            break;
+          }
+          g0 = g1;
+          g1 = fetch(g1);
+          p0 = load_pred(g0);
+        }
         const int stage = ring_slot(k);
         if (k >= NS) mbar_wait<400>(&s_empty[stage], (uint32_t)(ring_turn(k) - 1) & 1u, 1, k);
-        const int lb = k / a.nbands, band = k - lb * a.nbands;
         if (band == 0) {
           // units complete out of order, so the block that used this key slot NB blocks ago may still be in
           // flight (all its units are already staged, so it will finish without this producer)
@@ -246,10 +287,8 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
             if (++polls > (1u << 24)) mbar_stuck(2, k, 0);
           *busy = 1u;
         }
-        const int gblk = cta + lb * G;
         const int pair = gblk / nblocks, b = gblk - pair * nblocks;
         const int by = b / a.gw, bx = b - by * a.gw;
-        const short2 pred = a.mv[(size_t)pair * a.mv_plane + b];
         const int x2 = bx * BS + pred.x, y2 = by * BS + pred.y;
         const int valid = !(x2 < 0 || y2 < 0 || x2 + BS > a.w || y2 + BS > a.h);
         const int wx = x2 - a.R;
@@ -279,7 +318,6 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
   // displacement column x SEG rows).  A 32-lane work item is any aligned run of 32 lanes, so it may straddle two
   // consecutive units (IU >= 32): no lane idles at unit boundaries.  Completion is counted in lanes.
   const int IU = max(a.n * a.segs_per_band, 32);  // tiny search ranges: pad the unit to one full item (lanes past n * segs idle)
-  const int total_lanes = my_units * IU;
   auto finish_unit = [&](int stage) {  // lane 0 of the warp that completed the unit's last lane
     const StageMeta m = s_meta[stage];
     s_sdone[stage] = 0;
@@ -322,13 +360,16 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
   // same parity -- on a fresh barrier even on the "phase before the first".  The unit number in the stage's metadata
   // (written by the producer before it arms the barrier, hence visible once the barrier completes; -1 at start) tells
   // the turns apart.
-  auto wait_unit = [&](int k) {
+  // Returns false when unit k does not exist: the producer has run out of blocks and published the number of units it staged.
+  auto wait_unit = [&](int k) -> bool {
     const int st = ring_slot(k);
     const uint32_t par = (uint32_t)ring_turn(k) & 1u;
-    for (uint32_t polls = 0;; __nanosleep(64)) {
-      mbar_wait(&s_full[st], par, 3, k);
-      if (*reinterpret_cast<volatile int*>(&s_meta[st].unit) == k) break;
-      if (++polls > (1u << 24)) mbar_stuck(4, k, par);
+    for (uint32_t polls = 0;; ++polls) {
+      const bool phase = mbar_try(&s_full[st], par);  // a failed try has already waited in hardware
+      if (phase && *reinterpret_cast<volatile int*>(&s_meta[st].unit) == k) return true;
+      if (*reinterpret_cast<volatile int*>(&s_end) <= k) return false;
+      if (phase) __nanosleep(64);  // an older turn of the stage satisfies the parity: the try returns at once, do not spin on it
+      if (polls > (1u << 24)) mbar_stuck(4, k, par);
     }
   };
 
@@ -337,12 +378,10 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
     if (lane == 0) t = atomicAdd(&s_next, 1u);
     t = __shfl_sync(0xffffffffu, t, 0);
     const int T0 = (int)t * 32;
-    if (T0 >= total_lanes) break;
-    const int k0 = a.iu_magic ? (int)__umulhi((uint32_t)T0, a.iu_magic) : T0 / IU;  // unit of lane 0
+    const int k0 = a.iu_magic ? (int)(__umulhi((uint32_t)T0, a.iu_magic) >> a.iu_shift) : T0 / IU;  // unit of lane 0
+    if (!wait_unit(k0)) break;                           // past the CTA's last unit
     const int split = (k0 + 1) * IU - T0;                // lanes [0, split) belong to k0, the rest to k0 + 1
-    const int k1 = (split < 32 && k0 + 1 < my_units) ? k0 + 1 : k0;
-    wait_unit(k0);
-    if (k1 != k0) wait_unit(k1);
+    const int k1 = (split < 32 && wait_unit(k0 + 1)) ? k0 + 1 : k0;
 
     const int T = T0 + lane;
     const bool second = lane >= split;
@@ -351,8 +390,8 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
     const StageMeta m = s_meta[stage];
     const int q = T - kl * IU;
     const int segs_here = min(a.segs_per_band, a.segs_total - m.band * a.segs_per_band);
-    const int sidx_raw = a.n_magic ? (int)__umulhi((uint32_t)q, a.n_magic) : q / a.n;  // q >= 0
-    const bool active = T < total_lanes && (!second || k1 != k0) && m.valid && sidx_raw < segs_here;
+    const int sidx_raw = a.n_magic ? (int)(__umulhi((uint32_t)q, a.n_magic) >> a.n_shift) : q / a.n;  // q >= 0
+    const bool active = (!second || k1 != k0) && m.valid && sidx_raw < segs_here;
     const int sidx = active ? sidx_raw : 0, o = active ? q - sidx_raw * a.n : 0;
     uint32_t best = 0xffffffffu, best_rank = 0xffffffffu;  // K64: best = SAD, best_rank = its spiral rank
     uint32_t eqmask = 0;   // K64: the lane's candidates that attain `best`
@@ -794,7 +833,7 @@ again:
 }
 
 int launch_search_tma(const TmaSearchPlan& plan, ImgView i1, ImgView i2, MvView mv, int n,
-                      unsigned long long* counters, int sm_count, cudaStream_t s) {
+                      unsigned long long* counters, unsigned int* work_ctr, int sm_count, cudaStream_t s) {
   (void)i2;
   TmaGeom g;
   if (!plan.supported || !make_geom(i1.w, i1.h, plan.bs, plan.R, plan.pre != 0, &g) || g.pre != plan.pre) return -1;
@@ -807,11 +846,24 @@ int launch_search_tma(const TmaSearchPlan& plan, ImgView i1, ImgView i2, MvView 
   int grid = sm_count * kMinCtas;
   if (grid > total) grid = total;
   {
-    // exact multiply-high division (three integer divisions per 32-lane item otherwise): valid while dividend * divisor < 2^32
+    // exact multiply-high division (three integer divisions per 32-lane item otherwise): for d >= 2 and p = 31 + ceil(log2 d),
+    // m = ceil(2^p / d) < 2^32 and floor(x * m / 2^p) == x / d for every 0 <= x < 2^31
+    auto magic = [](unsigned d, uint32_t* m, uint32_t* sh) {
+      unsigned lg = 0;
+      while ((1ull << lg) < d) ++lg;
+      const unsigned p = 31 + lg;
+      *m = (uint32_t)(((1ull << p) + d - 1) / d);
+      *sh = p - 32;
+    };
     const unsigned long long iu = (unsigned long long)(a.n * a.segs_per_band > 32 ? a.n * a.segs_per_band : 32);
-    const unsigned long long units_per_cta = ((unsigned long long)total + grid - 1) / grid * a.nbands;
-    a.n_magic = (iu + 64) * (unsigned long long)a.n < (1ull << 32) ? (uint32_t)((1ull << 32) / (unsigned)a.n + 1) : 0u;
-    a.iu_magic = (units_per_cta * iu + 64) * iu < (1ull << 32) ? (uint32_t)((1ull << 32) / iu + 1) : 0u;
+    magic((unsigned)a.n, &a.n_magic, &a.n_shift);
+    magic((unsigned)iu, &a.iu_magic, &a.iu_shift);
+    // lanes of one CTA are numbered in 31 bits: with the counter one CTA could in principle take every block
+    const bool fits = (unsigned long long)total * a.nbands * iu + 64 < (1ull << 31);
+    static const bool force_static = getenv("BBME_SEARCH_STATIC") != nullptr;  // A-B runs: blocks strided by CTA index
+    a.work_ctr = fits && !force_static ? work_ctr : nullptr;
+    if (!fits && (((unsigned long long)total + grid - 1) / grid * a.nbands * iu + 64 >= (1ull << 31))) a.iu_magic = 0;  // divide
+    if (a.work_ctr && cudaMemsetAsync(a.work_ctr, 0, sizeof(unsigned int), s) != cudaSuccess) return -1;
   }
   return dispatch(plan, g.k64, a.pww, g.deep, &a, grid, s) == 1 ? 0 : -1;
 }
