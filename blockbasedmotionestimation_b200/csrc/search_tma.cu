@@ -5,18 +5,21 @@
 // block lies inside the image, minimum SAD, ties to the earliest position of the reference's spiral walk.
 //
 // How (B200-first, see DESIGN.md "search kernel"):
-//  * VABSDIFF4.U8.ACC issues at 64 lanes/clk/SM and shares its pipe with SHF/PRMT/LOP3 (bench_micro/int_peak.cu),
-//    so the inner loop is kept to SADs plus the unavoidable byte alignment: displacement dx shifts the window by
-//    single bytes, and TMA tile loads need a 16-byte-aligned innermost coordinate (an unaligned one raises an
-//    illegal-instruction fault -- scripts/tma_probe.cu), so the window is staged ONCE from the aligned origin
-//    below the wanted one and each lane funnel-shifts the TWW+1 aligned words of a row into TWW words: 4 SHF feed
-//    64 SADs (6 % of the pipe).
-//  * One warp is the TMA producer (a ring of kStages stages, mbarrier full/empty); eight consumer warps pull
-//    32-lane work items from a shared counter (balances the four SM sub-partitions without CTA barriers).
+//  * VABSDIFF4.U8.ACC issues at 64 lanes/clk/SM and shares its pipe with SHF/PRMT/LOP3 (bench_micro/int_peak.cu); IMAD.HI and
+//    IMAD.WIDE cost the same slot (bench_micro/shift_pipe.cu).  The inner loop is therefore SADs and shared loads only.
+//  * Byte alignment: displacement dx shifts the window by single bytes, the SADs work on aligned words, and TMA tile loads need a
+//    16-byte-aligned innermost coordinate (an unaligned one raises an illegal-instruction fault -- scripts/tma_probe.cu).
+//    PRE instantiations: image 2 exists in four copies shifted by 0..3 bytes (k_shift4, one HBM pass per level); one 4-D tile
+//    load stages a window as [row][byte phase][pitch] and a lane reads the phase of its column -- no shift instruction at all.
+//    The other instantiations (64-bit keys, pitch classes whose phases would collide in the banks, windows too large for four
+//    copies) stage the window once from the aligned origin and funnel-shift TWW+1 words of a row into TWW (13 % of the pipe).
+//  * One warp is the TMA producer (a ring of 5 / 8 / 16 stages, mbarrier full/empty); it takes blocks from a grid-wide counter,
+//    two ahead, and sleeps between polls of a full ring.  Sixteen consumer warps pull 32-lane work items from a shared counter
+//    (balances the four SM sub-partitions without CTA barriers).
 //  * A lane owns one displacement column dx and SEG consecutive dy: the 16x16 (or 8x8) block tile lives in 64
 //    (16) registers, SEG accumulators in registers, every window word loaded once per lane feeds up to 16 SADs.
 //  * The 32 lanes of a work item take consecutive dx, i.e. consecutive bytes: 8-9 distinct consecutive words per
-//    shared load, conflict-free.
+//    shared load (PRE: per byte phase, in disjoint bank groups).
 //  * Block results are reduced with a 32-bit key (SAD << KS | spiral rank); the ranks come from a table built once
 //    per CTA in shared memory, so the per-candidate epilogue is one 16-bit shared load, one IMAD and half a
 //    three-input min; warps reduce with redux.sync.min and one shared atomicMin per work item.
