@@ -68,7 +68,7 @@ struct TmaSearchArgs {
   int box_bytes;       // bytes of the window box
   int blk_bytes;       // bytes of the block box
   int stage_bytes;
-  int rank_off;        // byte offset of the spiral-rank table (uint16, (n + SEG) rows of n) in dynamic shared memory
+  int rank_off;        // byte offset of the spiral-rank table (uint16, (n + SEG) rows of 4 * pww) in dynamic shared memory
   int box1_word;       // 0: one window box; else the word column where the second (overlapping) box starts
   int box1_off_words;  // word offset of the second box inside a stage
   int stage_shift;     // log2(stages) when stages is a power of two, 0 when stages == kStages
@@ -235,13 +235,15 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  // spiral visit rank of every displacement, row-major [dy + R][dx + R]; rows past n hold 0xffff
+  // spiral visit rank of every displacement, [dy + R][dx + R] with a compile-time row pitch of NP >= n entries (the epilogue's
+  // thirteen rank loads then use immediate offsets instead of a chain of address adds); rows and columns past n hold 0xffff
   constexpr int KS = BS >= 32 ? 14 : 16;  // key = SAD << KS | rank; SAD < 2^(32-KS), rank < 2^KS (checked on the host)
+  constexpr int NP = 4 * PWW;             // n <= 4 * PWW - BS - 15 (the window of n + BS - 1 + 15 bytes fits the pitch)
   uint16_t* s_rank = reinterpret_cast<uint16_t*>(smem + a.rank_off);
   if (!K64) {
-    for (int i = threadIdx.x; i < (a.n + SEG) * a.n; i += blockDim.x) {
-      const int ry = i / a.n, rx = i - ry * a.n;
-      s_rank[i] = ry < a.n ? (uint16_t)spiral_rank(rx - a.R, ry - a.R) : (uint16_t)0xffffu;
+    for (int i = threadIdx.x; i < (a.n + SEG) * NP; i += blockDim.x) {
+      const int ry = i / NP, rx = i - ry * NP;
+      s_rank[i] = (ry < a.n && rx < a.n) ? (uint16_t)spiral_rank(rx - a.R, ry - a.R) : (uint16_t)0xffffu;
     }
   }
   __syncthreads();
@@ -486,14 +488,14 @@ k_search_tma(const __grid_constant__ CUtensorMap map_win, const __grid_constant_
         // (Tried for 8x8 blocks, where the two key instructions and the rank load per candidate are 13 % of an item: bare SAD
         // minima per lane and keys only in the lanes that hold the item's minimum after a warp reduction -- config 3 fell
         // from 65 % to 56 % of the integer peak: the 43 accumulators stay live across the reduction and the re-scan diverges.)
-        const uint16_t* rk = s_rank + (size_t)(m.band * a.band_rows + cy0) * a.n + o;
+        const uint16_t* rk = s_rank + (m.band * a.band_rows + cy0) * NP + o;
         if (xok && c_lo == 0 && c_hi == SEG - 1) {
 #pragma unroll
-          for (int c = 0; c < SEG; ++c) best = min(best, (acc[c] << KS) + (uint32_t)rk[c * a.n]);
+          for (int c = 0; c < SEG; ++c) best = min(best, (acc[c] << KS) + (uint32_t)rk[c * NP]);
         } else if (xok) {
 #pragma unroll
           for (int c = 0; c < SEG; ++c) {
-            const uint32_t key = (acc[c] << KS) + (uint32_t)rk[c * a.n];
+            const uint32_t key = (acc[c] << KS) + (uint32_t)rk[c * NP];
             best = (c >= c_lo && c <= c_hi) ? min(best, key) : best;
           }
         }
@@ -684,7 +686,7 @@ static bool make_geom_impl(int w, int h, int bs, int R, bool pre, TmaGeom* g) {
   const int segs_total = (n + seg - 1) / seg;
   const int blk_bytes = bs * (bs >= 16 ? bs : 16);
   // per stage: 24 KB, or what the CTA's 200 KB leave per stage next to the spiral-rank table
-  const size_t rank_bytes = use_k64 ? 0 : (((size_t)(n + seg) * n * 2 + 127) / 128) * 128;
+  const size_t rank_bytes = use_k64 ? 0 : (((size_t)(n + seg) * (4 * pww) * 2 + 127) / 128) * 128;  // rows of 4 * pww entries
   size_t budget = (cap - rank_bytes) / kStages / 128 * 128;
   if (!pre && budget > 24 * 1024) budget = 24 * 1024;
   int spb = segs_total;
@@ -721,8 +723,7 @@ static bool make_geom_impl(int w, int h, int bs, int R, bool pre, TmaGeom* g) {
   g->a.box1_off_words = two_box ? (int)(one_box / 4) : 0;
   // as deep a ring as the shared memory holds (the stage size above was chosen for kStages stages)
   {
-    const size_t rank_b = use_k64 ? 0 : (((size_t)(n + seg) * n * 2 + 127) / 128) * 128;
-    int st = (int)((cap - rank_b) / (size_t)g->a.stage_bytes);
+    int st = (int)((cap - rank_bytes) / (size_t)g->a.stage_bytes);
     // sixteen consumer warps want ~16 work items ready: a deep ring where a unit holds few items (32x32 / +-16: three), the
     // kStages that the large-window geometries were tuned with elsewhere (config 2 measured the same at 5, 8 and 16)
     const int items_per_unit = (n * spb + 31) / 32;
@@ -734,7 +735,7 @@ static bool make_geom_impl(int w, int h, int bs, int R, bool pre, TmaGeom* g) {
     g->a.stage_shift = g->a.stages == 16 ? 4 : (g->a.stages == 8 ? 3 : 0);
   }
   g->a.rank_off = g->a.stages * g->a.stage_bytes;
-  g->smem = (size_t)g->a.rank_off + (use_k64 ? 0 : (((size_t)(n + seg) * n * 2 + 127) / 128) * 128);
+  g->smem = (size_t)g->a.rank_off + rank_bytes;
   if (g->smem > cap) return false;  // ring + rank table must fit the CTA's shared memory: generic kernel instead
   g->pre = pre ? 1 : 0;
   return true;
