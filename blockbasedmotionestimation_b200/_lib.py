@@ -46,6 +46,11 @@ class BbmeHostLink(C.Structure):
                 ("host_stream_write_gbs", C.c_double), ("host_threads", C.c_int)]
 
 
+class BbmeSearchGeometry(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("planned", "copies", "deep_ring", "key64", "rows_per_lane", "pitch_words", "stages", "stage_bytes",
+                                       "smem_bytes", "bands", "segments_per_band", "box_w", "box_h", "two_boxes", "lanes_per_unit")]
+
+
 # name -> (restype, argtypes); every symbol include/bbme.h declares
 _P = C.c_void_p
 _I = C.c_int
@@ -97,6 +102,8 @@ SIGNATURES = {
     "bbme_host_free": (None, [_P]),
     "bbme_debug_skip_compute": (_I, [_P, _I]),
     "bbme_debug_set_stamp_epoch": (_I, [_P, C.c_uint32]),
+    "bbme_debug_search_geometry": (_I, [_I, _I, _I, _I, _I, C.POINTER(BbmeSearchGeometry)]),
+    "bbme_debug_div_magic": (_I, [C.c_uint, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]),
     "bbme_debug_level_image": (_I, [_P, _I, _I, _I, _P]),
     "bbme_debug_level_mv": (_I, [_P, _I, _I, _I, _P]),
     "bbme_stage_pyrdown": (_I, [_P, _P, _I, _I, _P]),

@@ -56,6 +56,26 @@ def plan_shape(width, height, search_size, block_size, num_levels=None):
     return _shape_dict(sh)
 
 
+def search_geometry(level_width, level_height, block_size, search_size, allow_copies=True):
+    """How the search planner would run one pyramid level (kernel family, ring depth, shared memory); needs no GPU."""
+    lib = _lib.load()
+    g = _lib.BbmeSearchGeometry()
+    rc = lib.bbme_debug_search_geometry(int(level_width), int(level_height), int(block_size), int(search_size), int(bool(allow_copies)), C.byref(g))
+    if rc != 0:
+        raise BbmeError(rc, lib.bbme_status_string(rc).decode())
+    return {k: getattr(g, k) for k, _ in _lib.BbmeSearchGeometry._fields_}
+
+
+def div_magic(divisor):
+    """(magic, shift) of the search kernel's multiply-high division: x // d == ((x * magic) >> 32) >> shift for 0 <= x < 2**31."""
+    lib = _lib.load()
+    m, s = C.c_uint(), C.c_uint()
+    rc = lib.bbme_debug_div_magic(int(divisor), C.byref(m), C.byref(s))
+    if rc != 0:
+        raise BbmeError(rc, lib.bbme_status_string(rc).decode())
+    return m.value, s.value
+
+
 class PyramidLevel:
     """pyramid_level.h:7-16 -- per-level state; images/flow are fetched from the device on demand."""
 

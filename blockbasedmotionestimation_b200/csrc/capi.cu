@@ -786,6 +786,25 @@ int bbme_debug_set_stamp_epoch(bbme_ctx* c, uint32_t epoch) {
   return BBME_OK;
 }
 
+int bbme_debug_search_geometry(int level_width, int level_height, int block_size, int search_size, int allow_copies,
+                               bbme_search_geometry* out) {
+  if (!out || level_width < 1 || level_height < 1 || !is_pow2(block_size) || search_size < block_size) return BBME_E_ARG;
+  static_assert(sizeof(bbme_search_geometry) == sizeof(TmaGeomInfo), "bbme_search_geometry mirrors TmaGeomInfo field by field");
+  TmaGeomInfo gi;
+  tma_search_geometry(level_width, level_height, block_size, radius_of(search_size, block_size), allow_copies, &gi);
+  memcpy(out, &gi, sizeof(gi));
+  return BBME_OK;
+}
+
+int bbme_debug_div_magic(unsigned divisor, unsigned* magic, unsigned* shift) {
+  if (divisor < 2 || !magic || !shift) return BBME_E_ARG;
+  uint32_t m, s;
+  tma_div_magic(divisor, &m, &s);
+  *magic = m;
+  *shift = s;
+  return BBME_OK;
+}
+
 int bbme_debug_skip_compute(bbme_ctx* c, int on) {
   if (!c) return BBME_E_ARG;
   c->skip_compute = on != 0;

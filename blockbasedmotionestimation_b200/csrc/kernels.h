@@ -99,6 +99,13 @@ struct TmaSearchPlan {
 int tma_search_plan(TmaSearchPlan* plan, const uint8_t* img1, const uint8_t* img2, const uint8_t* img2_shift4, int w, int h,
                     int pitch, size_t plane, int n_planes, int bs, int R, char* err, size_t errlen);
 int tma_search_wants_pre(int w, int h, int bs, int R);
+// Host-only views of the planner, for tests that run without a GPU (bbme_debug_search_geometry / bbme_debug_div_magic).
+struct TmaGeomInfo {
+  int planned, copies, deep_ring, key64, rows_per_lane, pitch_words, stages, stage_bytes, smem_bytes, bands, segments_per_band,
+      box_w, box_h, two_boxes, lanes_per_unit;
+};
+int tma_search_geometry(int w, int h, int bs, int R, int allow_copies, TmaGeomInfo* out);  // 0: the generic kernel's geometry
+void tma_div_magic(unsigned d, uint32_t* magic, uint32_t* shift);  // x / d == umulhi(x, magic) >> shift for 0 <= x < 2^31, d >= 2
 void launch_shift4(ImgView src, uint8_t* dst, int n, cudaStream_t s);
 // work_ctr: one device word owned by the caller's stream (zeroed here, then the kernel's block counter); nullptr = blocks strided by CTA
 int launch_search_tma(const TmaSearchPlan& plan, ImgView i1, ImgView i2, MvView mv, int n,

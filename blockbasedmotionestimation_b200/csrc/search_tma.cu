@@ -751,6 +751,36 @@ static bool make_geom(int w, int h, int bs, int R, bool want_pre, TmaGeom* g) {
   return make_geom_impl(w, h, bs, R, false, g);
 }
 
+void tma_div_magic(unsigned d, uint32_t* m, uint32_t* sh) {
+  unsigned lg = 0;
+  while ((1ull << lg) < d) ++lg;
+  const unsigned p = 31 + lg;
+  *m = (uint32_t)(((1ull << p) + d - 1) / d);
+  *sh = p - 32;
+}
+
+int tma_search_geometry(int w, int h, int bs, int R, int allow_copies, TmaGeomInfo* out) {
+  TmaGeom g;
+  memset(out, 0, sizeof(*out));
+  if (!make_geom(w, h, bs, R, allow_copies != 0, &g)) return 0;
+  out->planned = 1;
+  out->copies = g.pre;
+  out->deep_ring = g.deep;
+  out->key64 = g.k64;
+  out->rows_per_lane = g.seg;
+  out->pitch_words = g.a.pww;
+  out->stages = g.a.stages;
+  out->stage_bytes = g.a.stage_bytes;
+  out->smem_bytes = (int)g.smem;
+  out->bands = g.a.nbands;
+  out->segments_per_band = g.a.segs_per_band;
+  out->box_w = g.box_w;
+  out->box_h = g.box_h;
+  out->two_boxes = g.a.box1_word != 0;
+  out->lanes_per_unit = g.a.n * g.a.segs_per_band > 32 ? g.a.n * g.a.segs_per_band : 32;
+  return 1;
+}
+
 int tma_search_wants_pre(int w, int h, int bs, int R) {
   TmaGeom g;
   return make_geom(w, h, bs, R, true, &g) && g.pre;
@@ -852,16 +882,9 @@ int launch_search_tma(const TmaSearchPlan& plan, ImgView i1, ImgView i2, MvView 
   {
     // exact multiply-high division (three integer divisions per 32-lane item otherwise): for d >= 2 and p = 31 + ceil(log2 d),
     // m = ceil(2^p / d) < 2^32 and floor(x * m / 2^p) == x / d for every 0 <= x < 2^31
-    auto magic = [](unsigned d, uint32_t* m, uint32_t* sh) {
-      unsigned lg = 0;
-      while ((1ull << lg) < d) ++lg;
-      const unsigned p = 31 + lg;
-      *m = (uint32_t)(((1ull << p) + d - 1) / d);
-      *sh = p - 32;
-    };
     const unsigned long long iu = (unsigned long long)(a.n * a.segs_per_band > 32 ? a.n * a.segs_per_band : 32);
-    magic((unsigned)a.n, &a.n_magic, &a.n_shift);
-    magic((unsigned)iu, &a.iu_magic, &a.iu_shift);
+    tma_div_magic((unsigned)a.n, &a.n_magic, &a.n_shift);
+    tma_div_magic((unsigned)iu, &a.iu_magic, &a.iu_shift);
     // lanes of one CTA are numbered in 31 bits: with the counter one CTA could in principle take every block
     const bool fits = (unsigned long long)total * a.nbands * iu + 64 < (1ull << 31);
     static const bool force_static = getenv("BBME_SEARCH_STATIC") != nullptr;  // A-B runs: blocks strided by CTA index

@@ -27,7 +27,7 @@ extern "C" {
 #endif
 
 #define BBME_MAX_LEVELS 16
-#define BBME_VERSION 200
+#define BBME_VERSION 201
 
 typedef enum {
   BBME_OK = 0,
@@ -243,6 +243,24 @@ int bbme_debug_skip_compute(bbme_ctx* ctx, int on);
 /* Test aid: sets the per-pair epoch of the regularisation's de-duplication stamps (a 32-bit counter that grows by a few
  * hundred per chunk for the lifetime of a plan; the kernel clears the stamps and restarts it before it can wrap). */
 int bbme_debug_set_stamp_epoch(bbme_ctx* ctx, uint32_t epoch);
+/* Test aids that need no GPU: how the search planner would run one pyramid level (which kernel family, ring, shared memory), and
+ * the multiply-high constants the search kernel divides with (x / d == (uint64(x) * magic >> 32) >> shift for 0 <= x < 2^31). */
+typedef struct bbme_search_geometry {
+  int planned;            /* 0: not a TMA-kernel geometry (the generic kernel runs it); the other fields are 0 then */
+  int copies;             /* 1: the kernel reads four byte-shifted copies of image 2 (no funnel shifts in the SAD loop) */
+  int deep_ring;          /* 1: ring of 8 or 16 stages (few work items per unit) */
+  int key64;              /* 1: 64-bit (SAD, spiral rank) keys */
+  int rows_per_lane;      /* candidate rows per lane (SEG) */
+  int pitch_words;        /* window row pitch class in 32-bit words */
+  int stages, stage_bytes, smem_bytes;
+  int bands, segments_per_band;
+  int box_w, box_h;       /* TMA box of one window copy: bytes x rows */
+  int two_boxes;          /* window wider than one 256-byte TMA box */
+  int lanes_per_unit;
+} bbme_search_geometry;
+int bbme_debug_search_geometry(int level_width, int level_height, int block_size, int search_size, int allow_copies,
+                               bbme_search_geometry* out);
+int bbme_debug_div_magic(unsigned divisor, unsigned* magic, unsigned* shift);
 
 /* ---- state of the last bbme_estimate* call on slot 0, for per-stage parity tests (host output buffers) ---- */
 /* frame: 0 = image1, 1 = image2.  out: level_height x level_width bytes, dense. */

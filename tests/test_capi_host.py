@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
     exported = set(re.findall(r" T (bbme_[a-z0-9_]+)", out))
     assert set(declared) <= exported, sorted(set(declared) - exported)
     assert set(declared) == set(_lib.SIGNATURES), sorted(set(declared) ^ set(_lib.SIGNATURES))
-    assert lib.bbme_version() == 200
+    assert lib.bbme_version() == 201
 
 
 def test_library_contains_sm100a_code_only():
