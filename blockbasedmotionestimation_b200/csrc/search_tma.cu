@@ -870,7 +870,10 @@ int launch_search_tma(const TmaSearchPlan& plan, ImgView i1, ImgView i2, MvView 
                       unsigned long long* counters, unsigned int* work_ctr, int sm_count, cudaStream_t s) {
   (void)i2;
   TmaGeom g;
-  if (!plan.supported || !make_geom(i1.w, i1.h, plan.bs, plan.R, plan.pre != 0, &g) || g.pre != plan.pre) return -1;
+  if (!plan.supported || !make_geom(i1.w, i1.h, plan.bs, plan.R, plan.pre != 0, &g)) return -1;
+  // the geometry is recomputed here; a tuning variable changed between plan and launch must not pair one geometry's arguments
+  // with another's instantiation or shared-memory size
+  if (g.pre != plan.pre || g.seg != plan.seg || g.a.stages != plan.stages || g.smem != plan.smem_bytes || g.box_h != plan.box_h) return -1;
   TmaSearchArgs a = g.a;
   a.n_pairs = n;
   a.mv = mv.p;
